@@ -1,0 +1,218 @@
+/*
+ * shepseg_b200.h -- C ABI of libshepseg_b200.so, the B200 (sm_100a) implementation of
+ * pyshepseg's Shepherd-segmentation hot path.
+ *
+ * The reference (ubarsc/pyshepseg 2.0.3) is pure Python + numba and has no FFI of its
+ * own: the path is reached through the Python functions of pyshepseg/shepseg.py and
+ * pyshepseg/tiling.py.  Each entry point below therefore cites the reference FUNCTION it
+ * replaces; pyshepseg_b200/shepseg.py and pyshepseg_b200/tiling.py bind them with ctypes
+ * behind the reference's own signatures (see INTEGRATION.md for the stub a maintainer
+ * would add to the reference).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *  - every function returns 0 on success or an SSG_ERR_* code; the message is kept per
+ *    context and read with ssg_last_error(); nothing throws across the boundary;
+ *  - "host" pointers are caller-owned C-contiguous memory (pageable or pinned; pinned
+ *    memory obtained from ssg_host_alloc makes the copies asynchronous and full speed);
+ *    "device" pointers are CUDA device memory on the context's device;
+ *  - images are band-sequential (nBands, nRows, nCols) like the reference's `img`
+ *    (shepseg.py:140); label rasters are uint32 (nRows, nCols), 0 = null (shepseg.py:97-101);
+ *  - a context owns one CUDA stream and its scratch memory, is bound to one device and
+ *    must be used by one host thread at a time (use one context per worker thread, as the
+ *    reference uses one worker per tile, tiling.py:1548-1613);
+ *  - there is no CPU fallback: a context cannot be created without a CUDA device.
+ */
+#ifndef SHEPSEG_B200_H
+#define SHEPSEG_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSG_ABI_VERSION 1
+
+/* image element types (numpy dtypes the reference is used with) */
+#define SSG_U8 0
+#define SSG_U16 1
+#define SSG_I16 2
+
+#define SSG_OK 0
+#define SSG_ERR_ARG 1       /* bad argument (shape, dtype, null pointer, too many bands) */
+#define SSG_ERR_CUDA 2      /* CUDA runtime error; ssg_last_error() has the string */
+#define SSG_ERR_NOMEM 3     /* device or pinned allocation failed */
+#define SSG_ERR_STATE 4     /* call sequence error (e.g. no resident tile) */
+
+#define SSG_MAX_BANDS 16
+#define SSG_MAX_CLUSTERS 1024
+
+typedef struct ssg_ctx ssg_ctx;
+
+/* ---- library / context -------------------------------------------------------------- */
+int ssg_abi_version(void);
+int ssg_device_count(void);
+int ssg_ctx_create(int device, ssg_ctx **out);
+void ssg_ctx_destroy(ssg_ctx *ctx);
+const char *ssg_last_error(const ssg_ctx *ctx);
+/* the context's cudaStream_t, so a caller can order its own work / events against it */
+void *ssg_ctx_stream(ssg_ctx *ctx);
+int ssg_ctx_synchronize(ssg_ctx *ctx);
+/* pinned host memory for full-speed asynchronous copies */
+int ssg_host_alloc(size_t bytes, void **out);
+int ssg_host_free(void *p);
+
+/* ---- stage-level entry points: host buffers in, host buffers out --------------------- */
+
+/* shepseg.applySpectralClusters (shepseg.py:317-361): out[p] = 1 + index of the nearest
+ * centre (float64 ||c||^2 - 2 x.c, first minimum), 0 where any band equals nullVal. */
+int ssg_assign(ssg_ctx *ctx, const void *img, int dtype, int nBands, int64_t nRows,
+               int64_t nCols, const double *centres, int k, int hasNull, double nullVal,
+               int32_t *out);
+
+/* shepseg.clump (shepseg.py:452-541) including its MAX_CLUMP_SIZE=10000 splitting rule
+ * and raster-scan numbering from clumpId; *nextId = highest id used + 1. */
+int ssg_clump(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int64_t nCols,
+              int32_t ignoreVal, int fourConnected, uint32_t clumpId, uint32_t *out,
+              uint32_t *nextId);
+
+/* shepseg.makeSegSize (shepseg.py:544-569): segSize must hold max(seg)+1 entries. */
+int ssg_make_seg_size(ssg_ctx *ctx, const uint32_t *seg, int64_t nPixels, uint32_t *segSize,
+                      int64_t len);
+
+/* shepseg.eliminateSinglePixels (shepseg.py:572-615): seg and segSize are updated in
+ * place exactly as the reference leaves them (segSize stale after the final relabel). */
+int ssg_eliminate_single_pixels(ssg_ctx *ctx, const void *img, int dtype, int nBands,
+                                int64_t nRows, int64_t nCols, uint32_t *seg,
+                                uint32_t *segSize, int64_t len, uint32_t minSegId,
+                                int fourConnected, int64_t *numMoved);
+
+/* shepseg.eliminateSmallSegments (shepseg.py:918-1000).  spectralThreshold is
+ * maxSpectralDiff**2 evaluated in maxSpectralDiff's own type (float32 product for a
+ * numpy.float32, shepseg.py:1060) and widened to double by the caller. */
+int ssg_eliminate_small_segments(ssg_ctx *ctx, uint32_t *seg, const void *img, int dtype,
+                                 int nBands, int64_t nRows, int64_t nCols, uint32_t maxSegId,
+                                 int minSegSize, double spectralThreshold, int fourConnected,
+                                 uint32_t minSegId, int64_t *numEliminated);
+
+/* ---- the whole tile: shepseg.doShepherdSegmentation with kmeansObj given -------------- */
+typedef struct ssg_tile_params {
+    int dtype;             /* SSG_U8 / SSG_U16 / SSG_I16 */
+    int nBands;
+    int64_t nRows, nCols;
+    const double *centres; /* host, k x nBands row-major (kmeansObj.cluster_centers_) */
+    int k;
+    int hasNull;           /* imgNullVal is not None */
+    double nullVal;
+    int fourConnected;
+    int minSegSize;
+    double spectralThreshold;
+} ssg_tile_params;
+
+typedef struct ssg_tile_result {
+    uint32_t numClumps;             /* ids after clump (shepseg.py:214) */
+    uint32_t numSegments;           /* seg.max() of the final raster */
+    uint32_t singlePixelsEliminated;/* shepseg.py:226-227 */
+    int64_t smallSegmentsEliminated;/* shepseg.py:235 */
+    uint32_t numOversized;          /* connected components that hit MAX_CLUMP_SIZE */
+    uint32_t numSinglePixelRounds;
+    uint32_t numSmallPasses;
+    float msAssign, msClump, msSingle, msSmall, msTotal; /* device time of each stage */
+} ssg_tile_result;
+
+/* host image in, host labels out (segOut may be NULL: labels stay resident on the device
+ * for ssg_stitch_* / ssg_download_labels).  Copies are inside the call. */
+int ssg_segment_tile(ssg_ctx *ctx, const void *imgHost, const ssg_tile_params *prm,
+                     uint32_t *segOutHost, ssg_tile_result *res);
+/* device image in (already in HBM), labels stay on the device (segOutDev may be NULL to
+ * keep them in the context; otherwise a device pointer to nRows*nCols uint32). */
+int ssg_segment_tile_device(ssg_ctx *ctx, const void *imgDev, const ssg_tile_params *prm,
+                            uint32_t *segOutDev, ssg_tile_result *res);
+/* copy the resident labels of the last tile to host memory */
+int ssg_download_labels(ssg_ctx *ctx, uint32_t *segOutHost);
+/* device pointer of the resident labels of the last tile (owned by the context) */
+uint32_t *ssg_resident_labels(ssg_ctx *ctx);
+
+/* ---- tile stitching: tiling.stitchTiles / recodeTile / recodeSharedSegments /
+ *      relabelSegments / crossesMidline (tiling.py:950-1306) --------------------------
+ *
+ * The reference stitches tile after tile in row-major order, carrying a running maxSegId
+ * and the recoded overlap strips of the finished neighbours.  Here the per-pixel work is
+ * done on the device in two parallel phases around a tiny sequential resolve on the host
+ * (pyshepseg_b200/tiling.py), which is what lets tiles live on different GPUs:
+ *
+ *   ssg_tile_tables_device  per tile, independent of all other tiles' FINAL ids: bounding-box
+ *                           corner of every segment (relabelSegments, tiling.py:1255-1265),
+ *                           which segments cross the overlap midlines (crossesMidline,
+ *                           tiling.py:1271-1306), the rank of every segment the tile numbers
+ *                           itself (ascending id, tiling.py:1250-1267), and for the crossing
+ *                           segments the histogram of the neighbour tile's LOCAL labels under
+ *                           their strip pixels (the input of scipy.stats.mode, tiling.py:1194);
+ *   (host)                  lut = offset + rank; neighbour labels mapped through the
+ *                           neighbour's lut, counts of equal final ids added, mode taken
+ *                           (smallest id on ties), left overlap overriding top
+ *                           (tiling.py:1107-1121); offset = max(offset, max lut inside the
+ *                           trimmed window) (tiling.py:1042-1043);
+ *   ssg_apply_lut_device    out = lut[tile] over the trimmed window, straight into the mosaic
+ *                           (or a staging buffer) + histogram (tiling.py:1032-1035).
+ */
+typedef struct ssg_tile_tables {
+    uint32_t maxId;     /* largest label in the tile */
+    uint32_t countNew;  /* segments numbered by this tile (flag SSG_SEG_NUMBERED) */
+    uint32_t numPairs;  /* distinct (strip, segment, neighbour label) triples */
+    uint32_t reserved;
+} ssg_tile_tables;
+
+#define SSG_SEG_PRESENT 1u   /* id owns at least one pixel of the tile */
+#define SSG_SEG_NUMBERED 2u  /* numbered by this tile: lut = offset + rank */
+#define SSG_SEG_KEYTOP 4u    /* crosses the midline of the top overlap */
+#define SSG_SEG_KEYLEFT 8u   /* crosses the midline of the left overlap */
+#define SSG_SEG_INTRIM 16u   /* has a pixel inside the trimmed window */
+#define SSG_PAIR_LEFT (1ull << 63) /* pair key = strip bit | segment << 32 | neighbour label */
+
+/* tileDev: device labels (ysize, xsize) with contiguous ids 1..max.  topBDev / leftBDev:
+ * the labels of the upper / left neighbour under this tile's top `overlap` rows / left
+ * `overlap` columns (row strides in elements, so they may point into the neighbour's
+ * resident label raster), or NULL on the first tile row / column.  [top,bottom) x
+ * [left,right) is the trimmed window (tiling.py:997-1022).  Results stay in the context
+ * until the next call; sizes come back in *out. */
+int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
+                           int64_t overlap, const uint32_t *topBDev, int64_t topBStride,
+                           const uint32_t *leftBDev, int64_t leftBStride, int64_t top,
+                           int64_t bottom, int64_t left, int64_t right, ssg_tile_tables *out);
+/* rank[maxId+1] (1-based among the numbered segments, 0 otherwise), flags[maxId+1]
+ * (SSG_SEG_*), pairKeys[numPairs] ascending, pairCounts[numPairs]; host buffers. */
+int ssg_tile_tables_fetch(ssg_ctx *ctx, uint32_t *rank, uint8_t *flags, uint64_t *pairKeys,
+                          uint32_t *pairCounts);
+/* out[(r-top)*outStride + (c-left)] = lut[tile[r,c]] for the trimmed window; lutHost has
+ * maxId+1 entries.  outDev is device memory (a mosaic window or a staging buffer).  If
+ * histDev is not NULL, histDev[v] += 1 for every written value v < histLen. */
+int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
+                         const uint32_t *lutHost, uint32_t maxId, int64_t top, int64_t bottom,
+                         int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
+                         uint64_t *histDev, int64_t histLen);
+
+/* ---- plain device memory helpers (so the Python side needs nothing but ctypes) -------- */
+int ssg_dev_alloc(ssg_ctx *ctx, size_t bytes, void **out);
+int ssg_dev_free(ssg_ctx *ctx, void *p);
+int ssg_memcpy_h2d(ssg_ctx *ctx, void *dst, const void *src, size_t bytes);
+int ssg_memcpy_d2h(ssg_ctx *ctx, void *dst, const void *src, size_t bytes);
+int ssg_memcpy_d2d(ssg_ctx *ctx, void *dst, const void *src, size_t bytes);
+/* strided 2-D copies on the context's stream (rows of `widthBytes`, pitches in bytes) */
+int ssg_memcpy2d_d2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch,
+                     size_t widthBytes, size_t rows);
+int ssg_memcpy2d_d2h(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch,
+                     size_t widthBytes, size_t rows);
+int ssg_memcpy2d_h2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch,
+                     size_t widthBytes, size_t rows);
+int ssg_memset_d(ssg_ctx *ctx, void *dst, int value, size_t bytes);
+
+/* number of kernels this library has launched on the context since creation */
+uint64_t ssg_launch_count(const ssg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHEPSEG_B200_H */

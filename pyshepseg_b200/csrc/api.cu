@@ -1,0 +1,415 @@
+// api.cu -- the extern "C" boundary of libshepseg_b200.so (see include/shepseg_b200.h).
+// Context lifetime, host<->device staging for the stage-level entry points, and the fused
+// tile pipeline assign -> clump -> single pixels -> small segments -> relabel
+// (shepseg.doShepherdSegmentation, shepseg.py:130-249).
+#include "common.cuh"
+
+static thread_local std::string g_noCtxError;
+
+extern "C" {
+
+int ssg_abi_version(void) { return SSG_ABI_VERSION; }
+
+int ssg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ssg_ctx_create(int device, ssg_ctx **out)
+{
+    if (!out) return SSG_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return SSG_ERR_CUDA; }
+    if (device < 0 || device >= n) return SSG_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return SSG_ERR_CUDA; }
+    ssg_ctx *ctx = new ssg_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->numSMs = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SSG_ERR_CUDA; }
+    if (cudaMalloc(&ctx->counters.p, C_COUNT * sizeof(uint64_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return SSG_ERR_NOMEM; }
+    ctx->counters.cap = C_COUNT * sizeof(uint64_t);
+    cudaMemsetAsync(ctx->counters.p, 0, ctx->counters.cap, ctx->stream);
+    if (cudaMallocHost(&ctx->hostCounters, C_COUNT * sizeof(uint64_t)) != cudaSuccess) {
+        cudaFree(ctx->counters.p); cudaStreamDestroy(ctx->stream); delete ctx; return SSG_ERR_NOMEM;
+    }
+    for (auto &e : ctx->ev) cudaEventCreate(&e);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return SSG_OK;
+}
+
+void ssg_ctx_destroy(ssg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->img, &ctx->cluster, &ctx->label, &ctx->seg, &ctx->aux0, &ctx->aux1, &ctx->aux2,
+                      &ctx->segSize, &ctx->isum, &ctx->fsum, &ctx->listOff, &ctx->nextChunk, &ctx->tailChunk,
+                      &ctx->mergeTo, &ctx->pendHead, &ctx->pendNext, &ctx->candList, &ctx->targetList, &ctx->lut,
+                      &ctx->flags, &ctx->blockCnt, &ctx->cubTemp, &ctx->sortKeys0, &ctx->sortKeys1, &ctx->sortVals0,
+                      &ctx->sortVals1, &ctx->emuStack, &ctx->centres, &ctx->counters, &ctx->stitch0, &ctx->stitch1,
+                      &ctx->stitch2, &ctx->stitch3, &ctx->stitch4, &ctx->stitch5};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->hostCounters) cudaFreeHost(ctx->hostCounters);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *ssg_last_error(const ssg_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void *ssg_ctx_stream(ssg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t ssg_launch_count(const ssg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+#define CTX_ENTER(ctx)                                                  \
+    if (!(ctx)) return SSG_ERR_ARG;                                     \
+    (ctx)->err.clear();                                                 \
+    SSG_CUDA(ctx, cudaSetDevice((ctx)->device))
+
+int ssg_ctx_synchronize(ssg_ctx *ctx)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+
+int ssg_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return SSG_ERR_ARG;
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return SSG_ERR_NOMEM; }
+    return SSG_OK;
+}
+
+int ssg_host_free(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return SSG_ERR_CUDA; }
+    return SSG_OK;
+}
+
+// ---- plain memory helpers --------------------------------------------------------------------
+int ssg_dev_alloc(ssg_ctx *ctx, size_t bytes, void **out)
+{
+    CTX_ENTER(ctx);
+    if (!out) SSG_FAIL(ctx, SSG_ERR_ARG, "null out pointer");
+    SSG_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return SSG_OK;
+}
+int ssg_dev_free(ssg_ctx *ctx, void *p)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (p) SSG_CUDA(ctx, cudaFree(p));
+    return SSG_OK;
+}
+int ssg_memcpy_h2d(ssg_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SSG_OK;
+}
+int ssg_memcpy_d2h(ssg_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+int ssg_memcpy_d2d(ssg_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SSG_OK;
+}
+int ssg_memcpy2d_d2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t widthBytes, size_t rows)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SSG_OK;
+}
+int ssg_memcpy2d_d2h(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t widthBytes, size_t rows)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+int ssg_memcpy2d_h2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t widthBytes, size_t rows)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->stream));
+    return SSG_OK;
+}
+int ssg_memset_d(ssg_ctx *ctx, void *dst, int value, size_t bytes)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return SSG_OK;
+}
+
+// ---- argument checks -------------------------------------------------------------------------
+static int check_image_args(ssg_ctx *ctx, const void *img, int dtype, int nBands, int64_t nRows, int64_t nCols)
+{
+    if (!img && nRows * nCols > 0) SSG_FAIL(ctx, SSG_ERR_ARG, "null image pointer");
+    if (dtype != SSG_U8 && dtype != SSG_U16 && dtype != SSG_I16) SSG_FAIL(ctx, SSG_ERR_ARG, "unsupported dtype code %d (uint8, uint16 and int16 images are supported)", dtype);
+    if (nBands < 1 || nBands > SSG_MAX_BANDS) SSG_FAIL(ctx, SSG_ERR_ARG, "nBands=%d not in 1..%d", nBands, SSG_MAX_BANDS);
+    if (nRows < 0 || nCols < 0) SSG_FAIL(ctx, SSG_ERR_ARG, "negative image size");
+    if (nRows * nCols >= 0x7FFFFFF0ll) SSG_FAIL(ctx, SSG_ERR_ARG, "tile of %lld pixels is too large (use the tiled entry point)", (long long)(nRows * nCols));
+    return SSG_OK;
+}
+
+static int upload_image(ssg_ctx *ctx, const void *imgHost, int dtype, int nBands, int64_t N)
+{
+    const size_t bytes = (size_t)N * nBands * dtypeSize(dtype);
+    SSG_TRY(ssg_reserve(ctx, ctx->img, bytes ? bytes : 16));
+    if (bytes) SSG_CUDA(ctx, cudaMemcpyAsync(ctx->img.p, imgHost, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SSG_OK;
+}
+
+// ---- stage-level entry points (host buffers) ---------------------------------------------------
+int ssg_assign(ssg_ctx *ctx, const void *img, int dtype, int nBands, int64_t nRows, int64_t nCols,
+               const double *centres, int k, int hasNull, double nullVal, int32_t *out)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(check_image_args(ctx, img, dtype, nBands, nRows, nCols));
+    if (!centres || (!out && nRows * nCols > 0)) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
+    const int64_t N = nRows * nCols;
+    if (N == 0) return SSG_OK;
+    SSG_TRY(upload_image(ctx, img, dtype, nBands, N));
+    SSG_TRY(ssg_reserve(ctx, ctx->cluster, (size_t)N * sizeof(int32_t)));
+    SSG_TRY(ssgk_assign(ctx, ctx->img.p, dtype, nBands, N, centres, k, hasNull, nullVal, bufp<int32_t>(ctx->cluster)));
+    SSG_CUDA(ctx, cudaMemcpyAsync(out, ctx->cluster.p, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+
+int ssg_clump(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int64_t nCols, int32_t ignoreVal,
+              int fourConnected, uint32_t clumpId, uint32_t *out, uint32_t *nextId)
+{
+    CTX_ENTER(ctx);
+    if (nRows < 0 || nCols < 0 || nRows * nCols >= 0x7FFFFFF0ll) SSG_FAIL(ctx, SSG_ERR_ARG, "bad raster size");
+    const int64_t N = nRows * nCols;
+    if (nextId) *nextId = clumpId;
+    if (N == 0) return SSG_OK;
+    if (!img || !out) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
+    SSG_TRY(ssg_reserve(ctx, ctx->cluster, (size_t)N * sizeof(int32_t)));
+    SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)N * sizeof(uint32_t)));
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->cluster.p, img, (size_t)N * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t numClumps = 0, numOver = 0;
+    SSG_TRY(ssgk_clump(ctx, bufp<int32_t>(ctx->cluster), nRows, nCols, ignoreVal, fourConnected, clumpId,
+                       bufp<uint32_t>(ctx->seg), &numClumps, &numOver));
+    SSG_CUDA(ctx, cudaMemcpyAsync(out, ctx->seg.p, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nextId) *nextId = clumpId + numClumps;
+    return SSG_OK;
+}
+
+int ssg_make_seg_size(ssg_ctx *ctx, const uint32_t *seg, int64_t nPixels, uint32_t *segSize, int64_t len)
+{
+    CTX_ENTER(ctx);
+    if (nPixels < 0 || len < 0 || (!seg && nPixels > 0) || (!segSize && len > 0)) SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument");
+    if (len == 0) return SSG_OK;
+    SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)(nPixels ? nPixels : 1) * sizeof(uint32_t)));
+    SSG_TRY(ssg_reserve(ctx, ctx->segSize, (size_t)len * sizeof(uint32_t)));
+    if (nPixels) SSG_CUDA(ctx, cudaMemcpyAsync(ctx->seg.p, seg, (size_t)nPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SSG_TRY(ssgk_seg_size(ctx, bufp<uint32_t>(ctx->seg), nPixels, bufp<uint32_t>(ctx->segSize), len));
+    SSG_CUDA(ctx, cudaMemcpyAsync(segSize, ctx->segSize.p, (size_t)len * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+
+int ssg_eliminate_single_pixels(ssg_ctx *ctx, const void *img, int dtype, int nBands, int64_t nRows,
+                                int64_t nCols, uint32_t *seg, uint32_t *segSize, int64_t len,
+                                uint32_t minSegId, int fourConnected, int64_t *numMoved)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(check_image_args(ctx, img, dtype, nBands, nRows, nCols));
+    const int64_t N = nRows * nCols;
+    if (numMoved) *numMoved = 0;
+    if (N == 0) return SSG_OK;
+    if (!seg || !segSize || len < 1) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
+    SSG_TRY(upload_image(ctx, img, dtype, nBands, N));
+    SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)N * sizeof(uint32_t)));
+    SSG_TRY(ssg_reserve(ctx, ctx->segSize, (size_t)len * sizeof(uint32_t)));
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->seg.p, seg, (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->segSize.p, segSize, (size_t)len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t moved = 0;
+    uint32_t rounds = 0, alive = 0;
+    SSG_TRY(ssgk_eliminate_single(ctx, ctx->img.p, dtype, nBands, nRows, nCols, bufp<uint32_t>(ctx->seg),
+                                  bufp<uint32_t>(ctx->segSize), len, fourConnected, &moved, &rounds));
+    // the reference leaves segSize as mergeSinglePixels updated it and relabels seg (shepseg.py:615)
+    SSG_CUDA(ctx, cudaMemcpyAsync(segSize, ctx->segSize.p, (size_t)len * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_TRY(ssgk_relabel(ctx, bufp<uint32_t>(ctx->seg), N, bufp<uint32_t>(ctx->segSize), len, minSegId, &alive));
+    SSG_CUDA(ctx, cudaMemcpyAsync(seg, ctx->seg.p, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (numMoved) *numMoved = moved;
+    return SSG_OK;
+}
+
+int ssg_eliminate_small_segments(ssg_ctx *ctx, uint32_t *seg, const void *img, int dtype, int nBands,
+                                 int64_t nRows, int64_t nCols, uint32_t maxSegId, int minSegSize,
+                                 double spectralThreshold, int fourConnected, uint32_t minSegId,
+                                 int64_t *numEliminated)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(check_image_args(ctx, img, dtype, nBands, nRows, nCols));
+    const int64_t N = nRows * nCols;
+    if (numEliminated) *numEliminated = 0;
+    if (N == 0) return SSG_OK;
+    if (!seg) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
+    if (minSegId != 1) SSG_FAIL(ctx, SSG_ERR_ARG, "minSegId must be 1 (shepseg.MINSEGID)");
+    const int64_t len = (int64_t)maxSegId + 1;
+    SSG_TRY(upload_image(ctx, img, dtype, nBands, N));
+    SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)N * sizeof(uint32_t)));
+    SSG_TRY(ssg_reserve(ctx, ctx->segSize, (size_t)len * sizeof(uint32_t)));
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->seg.p, seg, (size_t)N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SSG_TRY(ssgk_seg_size(ctx, bufp<uint32_t>(ctx->seg), N, bufp<uint32_t>(ctx->segSize), len));
+    int64_t numElim = 0;
+    uint32_t passes = 0, alive = 0;
+    SSG_TRY(ssgk_eliminate_small(ctx, ctx->img.p, dtype, nBands, nRows, nCols, bufp<uint32_t>(ctx->seg),
+                                 bufp<uint32_t>(ctx->segSize), maxSegId, minSegSize, spectralThreshold,
+                                 fourConnected, &numElim, &passes));
+    SSG_TRY(ssgk_relabel(ctx, bufp<uint32_t>(ctx->seg), N, bufp<uint32_t>(ctx->segSize), len, minSegId, &alive));
+    SSG_CUDA(ctx, cudaMemcpyAsync(seg, ctx->seg.p, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (numEliminated) *numEliminated = numElim;
+    return SSG_OK;
+}
+
+// ---- the fused tile pipeline -------------------------------------------------------------------
+__global__ void k_count_zero_sizes(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
+                                   unsigned long long *counter)
+{
+    const int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = s < len && segSize[s] == 0;
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
+}
+
+static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_params *prm,
+                             uint32_t *segDev, ssg_tile_result *res)
+{
+    const int64_t N = prm->nRows * prm->nCols;
+    memset(res, 0, sizeof(*res));
+    if (N == 0) return SSG_OK;
+    unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
+    SSG_TRY(ssg_reserve(ctx, ctx->cluster, (size_t)N * sizeof(int32_t)));
+
+    SSG_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    SSG_TRY(ssgk_assign(ctx, imgDev, prm->dtype, prm->nBands, N, prm->centres, prm->k, prm->hasNull,
+                        prm->nullVal, bufp<int32_t>(ctx->cluster)));
+    SSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    uint32_t numClumps = 0, numOver = 0;
+    SSG_TRY(ssgk_clump(ctx, bufp<int32_t>(ctx->cluster), prm->nRows, prm->nCols, 0, prm->fourConnected, 1,
+                       segDev, &numClumps, &numOver));
+    SSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    const int64_t len = (int64_t)numClumps + 1;
+    unsigned *segSize = bufp<unsigned>(ctx->segSize);
+
+    int64_t moved = 0;
+    uint32_t rounds = 0;
+    SSG_TRY(ssgk_eliminate_single(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev,
+                                  segSize, len, prm->fourConnected, &moved, &rounds));
+    // ids that lost their only pixel = what the reference reports as singlePixelsEliminated
+    // (oldMaxSegId - seg.max() after its order-preserving relabel, shepseg.py:226-227)
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, sizeof(unsigned long long), ctx->stream));
+    if (numClumps > 0) {
+        k_count_zero_sizes<<<gridFor(numClumps, 256), 256, 0, ctx->stream>>>(segSize, 1, len, counters + C_SCRATCH1);
+        SSG_LAUNCHED(ctx);
+    }
+    SSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+
+    // ids are not compacted between the two elimination stages: the reference's relabel is
+    // order preserving, so the merge order (ascending id) is unchanged
+    int64_t numElim = 0;
+    uint32_t passes = 0, alive = 0;
+    SSG_TRY(ssgk_eliminate_small(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev, segSize,
+                                 numClumps, prm->minSegSize, prm->spectralThreshold, prm->fourConnected,
+                                 &numElim, &passes));
+    SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &alive));
+    SSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    SSG_TRY(ssg_fetch_counters(ctx));
+
+    res->numClumps = numClumps;
+    res->numOversized = numOver;
+    res->numSegments = alive;
+    res->singlePixelsEliminated = (uint32_t)ctx->hostCounters[C_SCRATCH1];
+    res->smallSegmentsEliminated = numElim;
+    res->numSinglePixelRounds = rounds;
+    res->numSmallPasses = passes;
+    cudaEventElapsedTime(&res->msAssign, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&res->msClump, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&res->msSingle, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&res->msSmall, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&res->msTotal, ctx->ev[0], ctx->ev[4]);
+    return SSG_OK;
+}
+
+static int check_tile_params(ssg_ctx *ctx, const void *img, const ssg_tile_params *prm, ssg_tile_result *res)
+{
+    if (!prm || !res) SSG_FAIL(ctx, SSG_ERR_ARG, "null params/result");
+    SSG_TRY(check_image_args(ctx, img, prm->dtype, prm->nBands, prm->nRows, prm->nCols));
+    if (!prm->centres) SSG_FAIL(ctx, SSG_ERR_ARG, "null centres");
+    if (prm->k < 1 || prm->k > SSG_MAX_CLUSTERS) SSG_FAIL(ctx, SSG_ERR_ARG, "k=%d not in 1..%d", prm->k, SSG_MAX_CLUSTERS);
+    return SSG_OK;
+}
+
+int ssg_segment_tile_device(ssg_ctx *ctx, const void *imgDev, const ssg_tile_params *prm,
+                            uint32_t *segOutDev, ssg_tile_result *res)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(check_tile_params(ctx, imgDev, prm, res));
+    const int64_t N = prm->nRows * prm->nCols;
+    uint32_t *segDev = segOutDev;
+    if (!segDev) {
+        SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)(N ? N : 1) * sizeof(uint32_t)));
+        segDev = bufp<uint32_t>(ctx->seg);
+    }
+    SSG_TRY(segment_tile_impl(ctx, imgDev, prm, segDev, res));
+    ctx->resRows = prm->nRows;
+    ctx->resCols = prm->nCols;
+    ctx->haveResident = (segOutDev == nullptr);
+    return SSG_OK;
+}
+
+int ssg_segment_tile(ssg_ctx *ctx, const void *imgHost, const ssg_tile_params *prm,
+                     uint32_t *segOutHost, ssg_tile_result *res)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(check_tile_params(ctx, imgHost, prm, res));
+    const int64_t N = prm->nRows * prm->nCols;
+    SSG_TRY(upload_image(ctx, imgHost, prm->dtype, prm->nBands, N));
+    SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)(N ? N : 1) * sizeof(uint32_t)));
+    SSG_TRY(segment_tile_impl(ctx, ctx->img.p, prm, bufp<uint32_t>(ctx->seg), res));
+    ctx->resRows = prm->nRows;
+    ctx->resCols = prm->nCols;
+    ctx->haveResident = true;
+    if (segOutHost && N > 0) {
+        SSG_CUDA(ctx, cudaMemcpyAsync(segOutHost, ctx->seg.p, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SSG_OK;
+}
+
+int ssg_download_labels(ssg_ctx *ctx, uint32_t *segOutHost)
+{
+    CTX_ENTER(ctx);
+    if (!ctx->haveResident) SSG_FAIL(ctx, SSG_ERR_STATE, "no resident tile labels");
+    const int64_t N = ctx->resRows * ctx->resCols;
+    if (N > 0) {
+        SSG_CUDA(ctx, cudaMemcpyAsync(segOutHost, ctx->seg.p, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SSG_OK;
+}
+
+uint32_t *ssg_resident_labels(ssg_ctx *ctx)
+{
+    if (!ctx || !ctx->haveResident) return nullptr;
+    return bufp<uint32_t>(ctx->seg);
+}
+
+}  // extern "C"

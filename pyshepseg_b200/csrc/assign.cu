@@ -1,0 +1,259 @@
+// assign.cu -- K1: per-pixel nearest-centre assignment.
+// Replaces shepseg.applySpectralClusters (shepseg.py:317-361), i.e. scikit-learn's
+// KMeans.predict on the band-interleaved pixel matrix plus the +1 / null masking.
+//
+// Result contract (what the reference computes): argmin_j of the float64 value
+// ||c_j||^2 - 2 x.c_j, first minimum on ties, +1; 0 if any band equals imgNullVal.
+//
+// How it is done here: each thread takes V consecutive pixels of every band plane with one
+// wide load per band (coalesced, 16 B per lane for uint16 at V=8), the centres sit in
+// shared memory (float32 copy for the fast pass, float64 copy for the exact pass) and are
+// read as warp-wide broadcasts.  The fast pass evaluates sum_b (x_b - c_jb)^2 in float32
+// FFMA and tracks the best and second-best value.  Its rounding error is bounded by
+// E(D) = 2^-23 * (Cmax*sqrt(nB)*sqrt(D) + (nB+3)*D); whenever the best/second gap is inside
+// 4*E(D_second) + (float64 margin) the pixel is re-evaluated in float64 with exactly the
+// operation sequence of the oracle (separate multiply and add, no FMA), so the label equals
+// the float64 argmin in every case, ties included.
+#include "common.cuh"
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T *p, float (&x)[V])
+{
+    constexpr int BYTES = V * (int)sizeof(T);
+    if constexpr (BYTES == 16) {
+        uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (float)e[i];
+    } else if constexpr (BYTES == 8) {
+        uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (float)e[i];
+    } else if constexpr (BYTES == 4) {
+        unsigned r = __ldg(reinterpret_cast<const unsigned *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (float)e[i];
+    } else if constexpr (BYTES == 2 && V == 2) {
+        unsigned short r = __ldg(reinterpret_cast<const unsigned short *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (float)e[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (float)__ldg(p + i);
+    }
+}
+
+struct AssignBounds {
+    float alpha, beta, gamma;
+};
+
+// exact pass for one pixel: same float64 sequence as the oracle / scikit-learn form
+template <int NB>
+__device__ __noinline__ int assign_exact(const float (&x)[NB], const double *cd, const double *cn,
+                                         int k)
+{
+    int best = 0;
+    double bestD = 0.0;
+    for (int j = 0; j < k; j++) {
+        double dot = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            dot = __dadd_rn(dot, __dmul_rn((double)x[b], cd[j * NB + b]));
+        double d = __dadd_rn(cn[j], __dmul_rn(-2.0, dot));
+        if (j == 0 || d < bestD) { bestD = d; best = j; }
+    }
+    return best;
+}
+
+template <typename T, int NB, int V>
+__global__ void __launch_bounds__(256)
+k_assign(const T *__restrict__ img, int64_t N, const double *__restrict__ centres, int k,
+         int hasNull, double nullVal, AssignBounds bnd, int32_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    double *cd = reinterpret_cast<double *>(smemRaw);          // k*NB
+    double *cn = cd + (size_t)k * NB;                          // k
+    float *cf = reinterpret_cast<float *>(cn + k);             // k*NB
+
+    for (int i = threadIdx.x; i < k * NB; i += blockDim.x) {
+        double c = centres[i];
+        cd[i] = c;
+        cf[i] = (float)c;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; b++) s = __dadd_rn(s, __dmul_rn(cd[j * NB + b], cd[j * NB + b]));
+        cn[j] = s;
+    }
+    __syncthreads();
+
+    const int64_t nGroups = (N + V - 1) / V;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p0 = g * V;
+        float x[V][NB];
+        const bool full = (p0 + V <= N);
+        if (full) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                float t[V];
+                load_vec<T, V>(img + (size_t)b * N + p0, t);
+#pragma unroll
+                for (int v = 0; v < V; v++) x[v][b] = t[v];
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+#pragma unroll
+                for (int v = 0; v < V; v++)
+                    x[v][b] = (p0 + v < N) ? (float)__ldg(img + (size_t)b * N + p0 + v) : 0.0f;
+        }
+
+        float best[V], second[V];
+        int idx[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) { best[v] = 3.0e38f; second[v] = 3.0e38f; idx[v] = 0; }
+
+        for (int j = 0; j < k; j++) {
+            float c[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) c[b] = cf[j * NB + b];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    float df = x[v][b] - c[b];
+                    acc = fmaf(df, df, acc);
+                }
+                second[v] = fminf(second[v], fmaxf(acc, best[v]));
+                bool lt = acc < best[v];
+                best[v] = fminf(acc, best[v]);
+                idx[v] = lt ? j : idx[v];
+            }
+        }
+
+        int32_t res[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            float gap = second[v] - best[v];
+            float tol = 4.0f * (bnd.alpha * sqrtf(second[v]) + bnd.beta * second[v]) + bnd.gamma;
+            int lab = idx[v];
+            if (k > 1 && !(gap > tol)) {
+                float xv[NB];   // copy: keeps x[][] itself in registers
+#pragma unroll
+                for (int b = 0; b < NB; b++) xv[b] = x[v][b];
+                lab = assign_exact<NB>(xv, cd, cn, k);
+            }
+            bool isNull = false;
+            if (hasNull) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) isNull |= ((double)x[v][b] == nullVal);
+            }
+            res[v] = isNull ? 0 : lab + 1;
+        }
+        bool stored = false;
+        if constexpr (V == 8) {
+            if (full) {
+                int4 *o = reinterpret_cast<int4 *>(out + p0);
+                o[0] = make_int4(res[0], res[1], res[2], res[3]);
+                o[1] = make_int4(res[4], res[5], res[6], res[7]);
+                stored = true;
+            }
+        } else if constexpr (V == 4) {
+            if (full) {
+                *reinterpret_cast<int4 *>(out + p0) = make_int4(res[0], res[1], res[2], res[3]);
+                stored = true;
+            }
+        } else if constexpr (V == 2) {
+            if (full) {
+                *reinterpret_cast<int2 *>(out + p0) = make_int2(res[0], res[1]);
+                stored = true;
+            }
+        }
+        if (!stored) {
+#pragma unroll
+            for (int v = 0; v < V; v++)
+                if (p0 + v < N) out[p0 + v] = res[v];
+        }
+    }
+}
+
+template <typename T, int NB, int V>
+static int launch_assign(ssg_ctx *ctx, const void *img, int64_t N, const double *centresDev, int k,
+                         int hasNull, double nullVal, AssignBounds bnd, int32_t *out)
+{
+    size_t smem = (size_t)k * NB * (sizeof(double) + sizeof(float)) + (size_t)k * sizeof(double);
+    auto kern = k_assign<T, NB, V>;
+    if (smem > 48 * 1024)
+        SSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t nGroups = (N + V - 1) / V;
+    int64_t blocks = (nGroups + 255) / 256;
+    int64_t cap = (int64_t)ctx->numSMs * 64;   // grid-stride beyond this; keeps the centre prologue amortised
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, 256, smem, ctx->stream>>>(reinterpret_cast<const T *>(img), N, centresDev,
+                                                      k, hasNull, nullVal, bnd, out);
+    SSG_LAUNCHED(ctx);
+    return SSG_OK;
+}
+
+template <typename T, int NB>
+static int dispatch_v(ssg_ctx *ctx, const void *img, int64_t N, const double *centresDev, int k,
+                      int hasNull, double nullVal, AssignBounds bnd, int32_t *out)
+{
+    // widest load the alignment of every band plane allows
+    constexpr int VMAX = NB <= 4 ? 8 : (NB <= 8 ? 4 : 2);
+    const size_t planeBytes = (size_t)N * sizeof(T);
+    const bool aligned = ((uintptr_t)img % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                         (planeBytes % (VMAX * sizeof(T)) == 0);
+    if (aligned) return launch_assign<T, NB, VMAX>(ctx, img, N, centresDev, k, hasNull, nullVal, bnd, out);
+    return launch_assign<T, NB, 1>(ctx, img, N, centresDev, k, hasNull, nullVal, bnd, out);
+}
+
+template <typename T>
+static int dispatch_nb(ssg_ctx *ctx, const void *img, int nBands, int64_t N, const double *c, int k,
+                       int hasNull, double nullVal, AssignBounds bnd, int32_t *out)
+{
+    switch (nBands) {
+#define CASE(NB) case NB: return dispatch_v<T, NB>(ctx, img, N, c, k, hasNull, nullVal, bnd, out);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+        CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+    default: SSG_FAIL(ctx, SSG_ERR_ARG, "nBands=%d not in 1..%d", nBands, SSG_MAX_BANDS);
+    }
+}
+
+int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t N,
+                const double *centresHost, int k, int hasNull, double nullVal, int32_t *outDev)
+{
+    if (N == 0) return SSG_OK;
+    if (k < 1 || k > SSG_MAX_CLUSTERS) SSG_FAIL(ctx, SSG_ERR_ARG, "k=%d not in 1..%d", k, SSG_MAX_CLUSTERS);
+    const size_t nc = (size_t)k * nBands;
+    SSG_TRY(ssg_reserve(ctx, ctx->centres, nc * sizeof(double)));
+    // the caller's centre array may be reused as soon as we return: stage through a copy
+    // that lives until the stream has consumed it
+    ctx->centresStage.assign(centresHost, centresHost + nc);
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->centres.p, ctx->centresStage.data(), nc * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    const double *centresDev = bufp<double>(ctx->centres);
+    double cmax = 0.0;
+    for (size_t i = 0; i < nc; i++) { double a = fabs(centresHost[i]); if (a > cmax) cmax = a; }
+    const double xmax = dtype == SSG_U8 ? 255.0 : (dtype == SSG_U16 ? 65535.0 : 32768.0);
+    const double e23 = 1.0 / 8388608.0;
+    AssignBounds bnd;
+    bnd.alpha = (float)(e23 * (cmax + xmax * e23) * sqrt((double)nBands) * 1.01);
+    bnd.beta = (float)(e23 * (nBands + 3) * 1.01);
+    bnd.gamma = (float)(ldexp(1.0, -50) * (nBands + 2) * (nBands * cmax * cmax + 2.0 * nBands * xmax * cmax) + 1e-30);
+    switch (dtype) {
+    case SSG_U8: return dispatch_nb<uint8_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);
+    case SSG_U16: return dispatch_nb<uint16_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);
+    case SSG_I16: return dispatch_nb<int16_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);
+    default: SSG_FAIL(ctx, SSG_ERR_ARG, "unsupported dtype code %d", dtype);
+    }
+}

@@ -1,0 +1,463 @@
+// clump.cu -- K2: connected-component labelling with the reference's numbering.
+// Replaces shepseg.clump (shepseg.py:452-541) and shepseg.makeSegSize (544-569).
+//
+// Result contract: 4-/8-connected regions of equal value (ignoreVal skipped) are numbered
+// clumpId, clumpId+1, ... in the raster order of their first pixel; a region of more than
+// MAX_CLUMP_SIZE+1 = 10001 pixels is carved into pieces exactly as the reference's capped
+// LIFO flood fill carves it (shepseg.py:481,502,523-537).
+//
+// How it is done here
+//   1. ccl_local : union-find over a 64x32 pixel block in shared memory (atomicCAS linking to
+//                  the smaller index), roots written as global linear indices;
+//   2. ccl_border: unions across block borders in global memory;
+//   3. ccl_flatten: every pixel points at its root = the raster-first pixel of its region,
+//                  which is the reference's seed pixel;
+//   4. numbering : roots counted per 1024-pixel block, block offsets by an exclusive scan,
+//                  in-block ranks recomputed -> id = clumpId + rank of the root in raster
+//                  order; ids gathered to every pixel; sizes by warp-aggregated atomics;
+//   5. regions larger than 10001 pixels (none in ordinary imagery) take the slow path: their
+//                  pixels are sorted by (region, raster index) and one warp per region replays
+//                  the capped flood fill sequentially; its seeds then join the numbering.
+#include "common.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+#define CCL_TW 64
+#define CCL_TH 32
+#define CCL_THREADS 256
+#define CCL_PIX (CCL_TW * CCL_TH)
+#define SSG_UNVISITED 0xFFFFFFFEu
+#define NUM_BLOCK_PIX 1024   // pixels per numbering block (256 threads x 4 consecutive)
+
+// ---- union-find primitives ---------------------------------------------------------------
+__device__ __forceinline__ unsigned s_find(volatile unsigned *par, unsigned x)
+{
+    unsigned p = par[x];
+    while (p != x) { x = p; p = par[x]; }
+    return x;
+}
+
+__device__ __forceinline__ void s_union(unsigned *par, unsigned a, unsigned b)
+{
+    while (true) {
+        a = s_find(par, a);
+        b = s_find(par, b);
+        if (a == b) return;
+        if (a < b) { unsigned t = a; a = b; b = t; }   // link the larger root under the smaller
+        unsigned old = atomicCAS(&par[a], a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__device__ __forceinline__ unsigned g_find(const unsigned *L, unsigned x)
+{
+    unsigned p = __ldcg(L + x);
+    while (p != x) { x = p; p = __ldcg(L + x); }
+    return x;
+}
+
+__device__ __forceinline__ void g_union(unsigned *L, unsigned a, unsigned b)
+{
+    while (true) {
+        a = g_find(L, a);
+        b = g_find(L, b);
+        if (a == b) return;
+        if (a < b) { unsigned t = a; a = b; b = t; }
+        unsigned old = atomicCAS(&L[a], a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// ---- 1. block-local labelling --------------------------------------------------------------
+__global__ void __launch_bounds__(CCL_THREADS)
+k_ccl_local(const int32_t *__restrict__ img, int64_t nRows, int64_t nCols, int32_t ignoreVal,
+            int four, unsigned *__restrict__ label)
+{
+    __shared__ int32_t c[CCL_PIX];
+    __shared__ unsigned par[CCL_PIX];
+    const int64_t x0 = (int64_t)blockIdx.x * CCL_TW;
+    const int64_t y0 = (int64_t)blockIdx.y * CCL_TH;
+
+#pragma unroll
+    for (int m = 0; m < CCL_PIX / CCL_THREADS; m++) {
+        int i = threadIdx.x + m * CCL_THREADS;
+        int64_t gx = x0 + (i % CCL_TW), gy = y0 + (i / CCL_TW);
+        int32_t v = ignoreVal;
+        if (gx < nCols && gy < nRows) v = __ldg(img + gy * nCols + gx);
+        c[i] = v;
+        par[i] = i;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < CCL_PIX / CCL_THREADS; m++) {
+        int i = threadIdx.x + m * CCL_THREADS;
+        int lx = i % CCL_TW, ly = i / CCL_TW;
+        int32_t v = c[i];
+        if (v == ignoreVal) continue;
+        bool left = lx > 0 && c[i - 1] == v;
+        bool up = ly > 0 && c[i - CCL_TW] == v;
+        if (left) s_union(par, i, i - 1);
+        if (up) {
+            // when left, up-left and up are all the same value the up link is implied by
+            // the row above's own left link
+            bool implied = left && c[i - CCL_TW - 1] == v;
+            if (!implied) s_union(par, i, i - CCL_TW);
+        }
+        if (!four && ly > 0) {
+            // diagonals matter only when the orthogonal neighbours do not already connect
+            if (lx > 0 && c[i - CCL_TW - 1] == v && !left && !up) s_union(par, i, i - CCL_TW - 1);
+            if (lx < CCL_TW - 1 && c[i - CCL_TW + 1] == v && !up) s_union(par, i, i - CCL_TW + 1);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < CCL_PIX / CCL_THREADS; m++) {
+        int i = threadIdx.x + m * CCL_THREADS;
+        int64_t gx = x0 + (i % CCL_TW), gy = y0 + (i / CCL_TW);
+        if (gx >= nCols || gy >= nRows) continue;
+        unsigned out = SSG_NIL;
+        if (c[i] != ignoreVal) {
+            unsigned r = s_find(par, i);
+            out = (unsigned)((y0 + r / CCL_TW) * nCols + x0 + (r % CCL_TW));
+        }
+        label[gy * nCols + gx] = out;
+    }
+}
+
+// ---- 2. unions across block borders ----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ccl_border(const int32_t *__restrict__ img, int64_t nRows, int64_t nCols, int32_t ignoreVal,
+             int four, unsigned *label, int64_t nHB, int64_t nVB)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nH = nHB * nCols;
+    int64_t y, x;
+    bool horiz;
+    if (t < nH) { y = (t / nCols + 1) * CCL_TH; x = t % nCols; horiz = true; }
+    else {
+        int64_t u = t - nH;
+        if (u >= nVB * nRows) return;
+        x = (u / nRows + 1) * CCL_TW; y = u % nRows; horiz = false;
+    }
+    const int64_t p = y * nCols + x;
+    const int32_t v = __ldg(img + p);
+    if (v == ignoreVal) return;
+    if (horiz) {
+        // neighbours in the row above (other block row)
+        if (__ldg(img + p - nCols) == v) g_union(label, (unsigned)p, (unsigned)(p - nCols));
+        if (!four) {
+            if (x > 0 && __ldg(img + p - nCols - 1) == v) g_union(label, (unsigned)p, (unsigned)(p - nCols - 1));
+            if (x < nCols - 1 && __ldg(img + p - nCols + 1) == v) g_union(label, (unsigned)p, (unsigned)(p - nCols + 1));
+        }
+    } else {
+        // neighbours in the column to the left (other block column)
+        if (__ldg(img + p - 1) == v) g_union(label, (unsigned)p, (unsigned)(p - 1));
+        if (!four) {
+            if (y > 0 && __ldg(img + p - nCols - 1) == v) g_union(label, (unsigned)p, (unsigned)(p - nCols - 1));
+            if (y < nRows - 1 && __ldg(img + p + nCols - 1) == v) g_union(label, (unsigned)p, (unsigned)(p + nCols - 1));
+        }
+    }
+}
+
+// ---- 3. flatten -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ccl_flatten(unsigned *label, int64_t N)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    unsigned l = label[p];
+    if (l == SSG_NIL) return;
+    unsigned r = g_find(label, l);
+    if (r != l) label[p] = r;
+}
+
+// ---- 4. numbering ---------------------------------------------------------------------------
+// a pixel is a root (the seed of a clump) iff it points at itself
+__global__ void __launch_bounds__(256)
+k_count_roots(const unsigned *__restrict__ label, int64_t N, unsigned *__restrict__ blockCnt,
+              unsigned long long *counters)
+{
+    const int64_t base = (int64_t)blockIdx.x * NUM_BLOCK_PIX + (int64_t)threadIdx.x * 4;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int64_t p = base + i;
+        if (p < N && label[p] == (unsigned)p) cnt++;
+    }
+    __shared__ int wsum[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane_id() == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += wsum[w];
+        blockCnt[blockIdx.x] = (unsigned)tot;
+        if (tot) atomicAdd(&counters[C_NUM_ROOTS], (unsigned long long)tot);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_number_roots(const unsigned *__restrict__ label, int64_t N, const unsigned *__restrict__ blockOff,
+               unsigned clumpId, unsigned *__restrict__ seg)
+{
+    const int64_t base = (int64_t)blockIdx.x * NUM_BLOCK_PIX + (int64_t)threadIdx.x * 4;
+    bool isRoot[4];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int64_t p = base + i;
+        isRoot[i] = (p < N && label[p] == (unsigned)p);
+        cnt += isRoot[i];
+    }
+    // exclusive prefix of cnt over the block (raster order = thread order)
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += v;
+    }
+    __shared__ int wsum[8];
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) wbase += wsum[w];
+    unsigned id = clumpId + blockOff[blockIdx.x] + (unsigned)(wbase + incl - cnt);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (isRoot[i]) seg[base + i] = id++;
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_ids(const unsigned *__restrict__ label, int64_t N, unsigned *seg, unsigned *segSize)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned id = 0;
+    bool valid = p < N;
+    if (valid) {
+        unsigned l = label[p];
+        if (l == SSG_NIL) id = 0;
+        else if (l == (unsigned)p) id = seg[p];
+        else id = __ldcg(seg + l);   // written by k_number_roots (previous launch)
+        if (l != (unsigned)p) seg[p] = id;
+    }
+    // size histogram: one atomic per distinct id per warp
+    unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    unsigned peers = __match_any_sync(active, id);
+    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&segSize[id], (unsigned)__popc(peers));
+}
+
+__global__ void __launch_bounds__(256)
+k_count_oversized(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
+                  unsigned long long *counters)
+{
+    const int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool over = s < len && segSize[s] > SSG_MAX_CLUMP_SIZE + 1;
+    bool single = s < len && segSize[s] == 1;
+    unsigned mo = __ballot_sync(0xffffffffu, over);
+    unsigned ms = __ballot_sync(0xffffffffu, single);
+    if (lane_id() == 0) {
+        if (mo) atomicAdd(&counters[C_NUM_OVERSIZED], (unsigned long long)__popc(mo));
+        if (ms) atomicAdd(&counters[C_NUM_SINGLES], (unsigned long long)__popc(ms));
+    }
+}
+
+// labels (root pointers) -> dense ids in seg + size table; returns the number of roots
+static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t N, unsigned clumpId,
+                              unsigned *seg, unsigned *numRoots)
+{
+    unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
+    const int64_t nBlocks = (N + NUM_BLOCK_PIX - 1) / NUM_BLOCK_PIX;
+    SSG_TRY(ssg_reserve(ctx, ctx->blockCnt, (size_t)nBlocks * 2 * sizeof(unsigned)));
+    unsigned *blockCnt = bufp<unsigned>(ctx->blockCnt);
+    unsigned *blockOff = blockCnt + nBlocks;
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_ROOTS, 0, sizeof(unsigned long long), ctx->stream));
+    k_count_roots<<<(unsigned)nBlocks, 256, 0, ctx->stream>>>(label, N, blockCnt, counters);
+    SSG_LAUNCHED(ctx);
+    size_t tmpBytes = 0;
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, blockCnt, blockOff, (int)nBlocks, ctx->stream));
+    SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, blockCnt, blockOff, (int)nBlocks, ctx->stream));
+    ctx->launches++;
+    k_number_roots<<<(unsigned)nBlocks, 256, 0, ctx->stream>>>(label, N, blockOff, clumpId, seg);
+    SSG_LAUNCHED(ctx);
+    SSG_TRY(ssg_fetch_counters(ctx));
+    *numRoots = (unsigned)ctx->hostCounters[C_NUM_ROOTS];
+    const size_t len = (size_t)clumpId + *numRoots;
+    SSG_TRY(ssg_reserve(ctx, ctx->segSize, len * sizeof(unsigned)));
+    SSG_CUDA(ctx, cudaMemsetAsync(ctx->segSize.p, 0, len * sizeof(unsigned), ctx->stream));
+    k_gather_ids<<<gridFor(N, 256), 256, 0, ctx->stream>>>(label, N, seg, bufp<unsigned>(ctx->segSize));
+    SSG_LAUNCHED(ctx);
+    return SSG_OK;
+}
+
+// ---- 5. slow path: regions over the cap -------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_flag_oversized(const unsigned *__restrict__ segSize, int64_t len, unsigned char *flag)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < len) flag[s] = (s != 0 && segSize[s] > SSG_MAX_CLUMP_SIZE + 1) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_mark_unvisited(const unsigned *__restrict__ pix, int64_t M, unsigned *label)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) label[pix[i]] = SSG_UNVISITED;
+}
+
+// One warp replays the reference's capped flood fill over one region (shepseg.py:490-539).
+// Lane l looks at window cell (cx, cy) = (sx-1 + l/3, sy-1 + l%3): columns outer, rows inner,
+// which is the order the reference pushes neighbours in (shepseg.py:523-524).
+__global__ void __launch_bounds__(128)
+k_capped_fill(const int32_t *__restrict__ img, int64_t nRows, int64_t nCols, int four,
+              const unsigned *__restrict__ sortedPix, const unsigned *__restrict__ runStart,
+              unsigned numRuns, int64_t M, unsigned *label, unsigned *stackPool, unsigned stackCap)
+{
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= numRuns) return;
+    const unsigned lane = lane_id();
+    const int64_t lo = runStart[warp];
+    const int64_t hi = (warp + 1 < numRuns) ? (int64_t)runStart[warp + 1] : M;
+    volatile unsigned *vlabel = label;
+    unsigned *stack = stackPool + (size_t)warp * stackCap;
+    const int dx = (int)(lane / 3) - 1, dy = (int)(lane % 3) - 1;
+    const bool cellUsed = lane < 9 && (!four || dx == 0 || dy == 0);
+
+    for (int64_t b0 = lo; b0 < hi; b0 += 32) {
+        const int64_t i = b0 + lane;
+        const unsigned myPix = i < hi ? sortedPix[i] : 0u;
+        while (true) {
+            bool unvis = i < hi && vlabel[myPix] == SSG_UNVISITED;
+            unsigned m = __ballot_sync(0xffffffffu, unvis);
+            if (m == 0) break;
+            const int src = __ffs(m) - 1;
+            const unsigned seed = __shfl_sync(0xffffffffu, myPix, src);
+            const int32_t val = __ldg(img + seed);
+            unsigned sp = 1, n = 0;
+            if (lane == 0) { vlabel[seed] = seed; stack[0] = seed; }
+            __syncwarp();
+            while (sp > 0 && n < SSG_MAX_CLUMP_SIZE) {
+                sp--;
+                const unsigned q = ((volatile unsigned *)stack)[sp];
+                const int64_t sy = q / nCols, sx = q % nCols;
+                const int64_t cx = sx + dx, cy = sy + dy;
+                bool ok = cellUsed && cx >= 0 && cx < nCols && cy >= 0 && cy < nRows;
+                unsigned nb = 0;
+                if (ok) {
+                    nb = (unsigned)(cy * nCols + cx);
+                    ok = __ldg(img + nb) == val && vlabel[nb] == SSG_UNVISITED;
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    vlabel[nb] = seed;
+                    ((volatile unsigned *)stack)[sp + __popc(pm & ((1u << lane) - 1u))] = nb;
+                }
+                const unsigned cnt = __popc(pm);
+                sp += cnt;
+                n += cnt;
+                __syncwarp();
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static int split_oversized(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int64_t nCols, int four,
+                           unsigned *label, const unsigned *seg, int64_t sizeLen)
+{
+    const int64_t N = nRows * nCols;
+    SSG_TRY(ssg_reserve(ctx, ctx->flags, (size_t)sizeLen));
+    unsigned char *flag = bufp<unsigned char>(ctx->flags);
+    k_flag_oversized<<<gridFor(sizeLen, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), sizeLen, flag);
+    SSG_LAUNCHED(ctx);
+    // pixels of the flagged regions, grouped by region, raster order inside each region
+    const unsigned *pixSorted = nullptr, *runStart = nullptr;
+    int64_t M = 0;
+    unsigned numRuns = 0;
+    SSG_TRY(ssgk_group_pixels(ctx, seg, N, flag, &pixSorted, nullptr, &runStart, &M, &numRuns));
+    if (M == 0) return SSG_OK;
+    k_mark_unvisited<<<gridFor(M, 256), 256, 0, ctx->stream>>>(pixSorted, M, label);
+    SSG_LAUNCHED(ctx);
+    const unsigned stackCap = SSG_MAX_CLUMP_SIZE + 32;
+    SSG_TRY(ssg_reserve(ctx, ctx->emuStack, (size_t)numRuns * stackCap * sizeof(unsigned)));
+    const unsigned warpsPerBlock = 4;
+    k_capped_fill<<<(numRuns + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, 0, ctx->stream>>>(
+        img, nRows, nCols, four, pixSorted, runStart, numRuns, M, label, bufp<unsigned>(ctx->emuStack), stackCap);
+    SSG_LAUNCHED(ctx);
+    return SSG_OK;
+}
+
+// ---- driver ----------------------------------------------------------------------------------
+int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t nCols,
+               int32_t ignoreVal, int four, uint32_t clumpId, uint32_t *segDev,
+               uint32_t *numClumps, uint32_t *numOversized)
+{
+    const int64_t N = nRows * nCols;
+    *numClumps = 0;
+    *numOversized = 0;
+    if (N == 0) return SSG_OK;
+    if (N >= 0xFFFFFFF0ll) SSG_FAIL(ctx, SSG_ERR_ARG, "tile of %lld pixels is too large for 32-bit pixel indices", (long long)N);
+    SSG_TRY(ssg_reserve(ctx, ctx->label, (size_t)N * sizeof(unsigned)));
+    unsigned *label = bufp<unsigned>(ctx->label);
+    unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
+
+    dim3 grid((unsigned)((nCols + CCL_TW - 1) / CCL_TW), (unsigned)((nRows + CCL_TH - 1) / CCL_TH));
+    k_ccl_local<<<grid, CCL_THREADS, 0, ctx->stream>>>(clusterDev, nRows, nCols, ignoreVal, four, label);
+    SSG_LAUNCHED(ctx);
+    const int64_t nHB = (nRows - 1) / CCL_TH, nVB = (nCols - 1) / CCL_TW;
+    const int64_t nBorder = nHB * nCols + nVB * nRows;
+    if (nBorder > 0) {
+        k_ccl_border<<<gridFor(nBorder, 256), 256, 0, ctx->stream>>>(clusterDev, nRows, nCols, ignoreVal, four, label, nHB, nVB);
+        SSG_LAUNCHED(ctx);
+        k_ccl_flatten<<<gridFor(N, 256), 256, 0, ctx->stream>>>(label, N);
+        SSG_LAUNCHED(ctx);
+    }
+    unsigned numRoots = 0;
+    SSG_TRY(number_from_labels(ctx, label, N, clumpId, segDev, &numRoots));
+    // oversized regions / single-pixel clumps
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_OVERSIZED, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_count_oversized<<<gridFor(numRoots, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), (int64_t)clumpId,
+                                                                       (int64_t)clumpId + numRoots, counters);
+    SSG_LAUNCHED(ctx);
+    SSG_TRY(ssg_fetch_counters(ctx));
+    const unsigned nOver = (unsigned)ctx->hostCounters[C_NUM_OVERSIZED];
+    *numOversized = nOver;
+    if (nOver > 0) {
+        SSG_TRY(split_oversized(ctx, clusterDev, nRows, nCols, four, label, segDev, (int64_t)clumpId + numRoots));
+        SSG_TRY(number_from_labels(ctx, label, N, clumpId, segDev, &numRoots));
+        SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_OVERSIZED, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        k_count_oversized<<<gridFor(numRoots, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), (int64_t)clumpId,
+                                                                           (int64_t)clumpId + numRoots, counters);
+        SSG_LAUNCHED(ctx);
+        SSG_TRY(ssg_fetch_counters(ctx));
+    }
+    *numClumps = numRoots;
+    return SSG_OK;
+}
+
+// ---- makeSegSize on an arbitrary label raster (shepseg.py:544-569) -----------------------------
+__global__ void __launch_bounds__(256)
+k_seg_size(const unsigned *__restrict__ seg, int64_t N, unsigned *segSize, int64_t len)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = p < N;
+    unsigned id = valid ? seg[p] : 0;
+    if (valid && (int64_t)id >= len) valid = false;
+    unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    unsigned peers = __match_any_sync(active, id);
+    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&segSize[id], (unsigned)__popc(peers));
+}
+
+int ssgk_seg_size(ssg_ctx *ctx, const uint32_t *segDev, int64_t N, uint32_t *sizeDev, int64_t len)
+{
+    SSG_CUDA(ctx, cudaMemsetAsync(sizeDev, 0, (size_t)len * sizeof(unsigned), ctx->stream));
+    if (N == 0) return SSG_OK;
+    k_seg_size<<<gridFor(N, 256), 256, 0, ctx->stream>>>(segDev, N, sizeDev, len);
+    SSG_LAUNCHED(ctx);
+    return SSG_OK;
+}

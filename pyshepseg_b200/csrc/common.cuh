@@ -1,0 +1,205 @@
+// common.cuh -- context, scratch-memory and error plumbing shared by the kernels of
+// libshepseg_b200.so.  Device code here is sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/shepseg_b200.h"
+
+#define SSG_NIL 0xFFFFFFFFu          // "no pixel / no root / no chunk"
+#define SSG_MAX_CLUMP_SIZE 10000u    // shepseg.py:481
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+// One context per worker thread: a stream, named scratch buffers that only ever grow,
+// a few pinned words for device->host scalars, per-stage events.
+struct ssg_ctx {
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // N-sized arrays (N = pixels of the current tile)
+    DevBuf img;       // staged image when the caller gave host memory
+    DevBuf cluster;   // int32 cluster ids (assign -> clump); later scratch
+    DevBuf label;     // uint32 root pixel per pixel (clump); later scratch
+    DevBuf seg;       // uint32 segment ids
+    DevBuf aux0, aux1, aux2;   // N-sized scratch (lists, moves)
+    // per-segment tables
+    DevBuf segSize, isum, fsum, listOff, nextChunk, tailChunk, mergeTo, pendHead, pendNext,
+           candList, targetList, lut, flags;
+    DevBuf blockCnt;  // per-block counts for the numbering scan
+    DevBuf cubTemp;   // temp storage for the CUB scans / sorts
+    DevBuf sortKeys0, sortKeys1, sortVals0, sortVals1;   // slow paths (oversized, ordered sums)
+    DevBuf emuStack;
+    DevBuf centres;   // double k*nBands
+    std::vector<double> centresStage;
+    DevBuf counters;  // small device counter block (see enum Counter)
+    DevBuf stitch0, stitch1, stitch2, stitch3, stitch4, stitch5;
+
+    uint64_t *hostCounters = nullptr;   // pinned mirror of `counters`
+    cudaEvent_t ev[8] = {};
+
+    // stitch tables of the last ssg_tile_tables_device call
+    int64_t stitchLen = 0;
+    uint32_t stitchPairs = 0;
+    std::vector<uint32_t> lutStage;
+
+    // resident tile
+    int64_t resRows = 0, resCols = 0;
+    bool haveResident = false;
+};
+
+enum Counter {
+    C_NUM_ROOTS = 0,
+    C_NUM_OVERSIZED,
+    C_NUM_SINGLES,
+    C_NUM_MOVES,
+    C_NUM_LEFT,
+    C_NUM_ALIVE,
+    C_NUM_SMALLPIX,
+    C_NUM_BIGSUM,
+    C_NUM_ELIM,
+    C_NUM_CAND0,
+    C_NUM_CAND1,
+    C_NUM_TARGETS0,
+    C_NUM_TARGETS1,
+    C_NUM_PASSES,
+    C_MAXLABEL,
+    C_SCRATCH0,
+    C_SCRATCH1,
+    C_SCRATCH2,
+    C_SCRATCH3,
+    C_COUNT = 32
+};
+
+#define SSG_FAIL(ctx, code, ...)                                        \
+    do {                                                                \
+        char _b[512];                                                   \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                          \
+        (ctx)->err = _b;                                                \
+        return (code);                                                  \
+    } while (0)
+
+#define SSG_CUDA(ctx, call)                                             \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) {                                        \
+            char _b[512];                                               \
+            snprintf(_b, sizeof(_b), "%s:%d: %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(_e));                           \
+            (ctx)->err = _b;                                            \
+            return _e == cudaErrorMemoryAllocation ? SSG_ERR_NOMEM : SSG_ERR_CUDA; \
+        }                                                               \
+    } while (0)
+
+#define SSG_TRY(call)                                                   \
+    do {                                                                \
+        int _rc = (call);                                               \
+        if (_rc != SSG_OK) return _rc;                                  \
+    } while (0)
+
+// check the launch that has just been issued
+#define SSG_LAUNCHED(ctx)                                               \
+    do {                                                                \
+        (ctx)->launches++;                                              \
+        SSG_CUDA(ctx, cudaGetLastError());                              \
+    } while (0)
+
+// grow-only device buffer
+static inline int ssg_reserve(ssg_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return SSG_OK;
+    if (b.p) {
+        SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SSG_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;   // a little headroom: tiles of one run vary in size
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        cudaGetLastError();
+        SSG_FAIL(ctx, SSG_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes,
+                 cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return SSG_OK;
+}
+
+template <typename T>
+static inline T *bufp(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+static inline unsigned gridFor(int64_t n, int block)
+{
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+// copy the counter block to the pinned mirror and wait for it
+static inline int ssg_fetch_counters(ssg_ctx *ctx)
+{
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->hostCounters, ctx->counters.p, C_COUNT * sizeof(uint64_t),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+
+static inline size_t dtypeSize(int dt) { return dt == SSG_U8 ? 1 : 2; }
+
+// ---- device helpers ----------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// one atomicAdd per warp for a per-thread 0/1 vote; returns this thread's slot (valid only
+// where pred is true).  All 32 lanes of the warp must call it.
+__device__ __forceinline__ unsigned long long warp_claim(unsigned long long *counter, bool pred)
+{
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    unsigned long long base = 0;
+    if (m == 0) return 0;
+    int leader = __ffs(m) - 1;
+    if ((int)lane_id() == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+
+// Pixels whose segment is flagged (segFlag[seg[p]] != 0), grouped by segment with raster
+// order kept inside each segment.  Outputs live in ctx scratch until the next call:
+// pixSorted[M], keysSorted[M] (segment id of each entry, may be requested as nullptr),
+// runStart[numRuns] (index of the first entry of every segment).
+int ssgk_group_pixels(ssg_ctx *ctx, const unsigned *segDev, int64_t N, const unsigned char *segFlag,
+                      const unsigned **pixSorted, const unsigned **keysSorted,
+                      const unsigned **runStart, int64_t *M, unsigned *numRuns);
+
+// stage entry points implemented in the other translation units ------------------------
+int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t N,
+                const double *centresHost, int k, int hasNull, double nullVal, int32_t *outDev);
+int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t nCols,
+               int32_t ignoreVal, int four, uint32_t clumpId, uint32_t *segDev,
+               uint32_t *numClumps, uint32_t *numOversized);
+int ssgk_seg_size(ssg_ctx *ctx, const uint32_t *segDev, int64_t N, uint32_t *sizeDev, int64_t len);
+int ssgk_eliminate_single(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
+                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, int64_t len,
+                          int four, int64_t *numMoved, uint32_t *numRounds);
+int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
+                         int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, uint32_t maxSegId,
+                         int minSegSize, double thr, int four, int64_t *numElim,
+                         uint32_t *numPasses);
+int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
+                 uint32_t minSegId, uint32_t *numAlive);

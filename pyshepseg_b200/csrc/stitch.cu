@@ -1,0 +1,299 @@
+// stitch.cu -- K9: the device side of tile stitching.
+// Replaces the per-pixel work of tiling.recodeTile / recodeSharedSegments / crossesMidline /
+// relabelSegments / HistogramAccumulator (tiling.py:1066-1306, 1915-1963).  The reference
+// builds a numba Dict of every pixel of every segment twice per tile and loops over the
+// segments in Python; here each question the reference asks of those lists becomes a
+// per-segment reduction over the label raster:
+//   * "top-left corner of the segment's bounding box" (tiling.py:1255-1257)  -> atomicMin of
+//     row and column per segment, warp-aggregated;
+//   * "does it cross the overlap midline" (tiling.py:1303-1306)              -> min / max of the
+//     stitch-axis coordinate over the strip pixels of the segment;
+//   * "rank among the segments this tile numbers" (tiling.py:1250-1267)      -> exclusive scan of
+//     the numbered flags in ascending id;
+//   * "mode of the neighbour's labels under the segment" (tiling.py:1194)    -> (segment,
+//     neighbour label) pairs of the crossing segments, radix sorted and run-length encoded;
+//     the mode itself is taken on the host after mapping neighbour labels to final ids.
+#include "common.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+
+struct StitchTables {
+    unsigned *minRow, *minCol;     // bbox corner over the whole tile
+    unsigned *tMin, *tMax1;        // row extent inside the top strip (max stored +1)
+    unsigned *lMin, *lMax1;        // column extent inside the left strip
+    unsigned *inTrim;
+};
+
+__global__ void __launch_bounds__(256)
+k_tile_max(const unsigned *__restrict__ tile, int64_t N, unsigned long long *counters)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = p < N ? tile[p] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (lane_id() == 0 && v) atomicMax(&counters[C_MAXLABEL], (unsigned long long)v);
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, int64_t topRows,
+               int64_t leftCols, int64_t top, int64_t bottom, int64_t left, int64_t right,
+               StitchTables tb)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < ysize * xsize;
+    const unsigned s = valid ? tile[p] : 0u;
+    const bool use = valid && s != 0;
+    const unsigned active = __ballot_sync(0xffffffffu, use);
+    if (!use) return;
+    const unsigned r = (unsigned)(p / xsize), c = (unsigned)(p % xsize);
+    const unsigned peers = __match_any_sync(active, s);
+    const bool leader = (int)lane_id() == __ffs(peers) - 1;
+    // a warp spans at most two raster rows, so reduce both coordinates over the peers
+    const unsigned rMin = __reduce_min_sync(peers, r), cMin = __reduce_min_sync(peers, c);
+    const bool inTop = r < topRows, inLeft = c < leftCols;
+    const unsigned tLo = __reduce_min_sync(peers, inTop ? r : SSG_NIL);
+    const unsigned tHi = __reduce_max_sync(peers, inTop ? r + 1 : 0u);
+    const unsigned lLo = __reduce_min_sync(peers, inLeft ? c : SSG_NIL);
+    const unsigned lHi = __reduce_max_sync(peers, inLeft ? c + 1 : 0u);
+    const bool trim = r >= top && r < bottom && c >= left && c < right;
+    const unsigned anyTrim = __reduce_max_sync(peers, trim ? 1u : 0u);
+    if (leader) {
+        atomicMin(&tb.minRow[s], rMin);
+        atomicMin(&tb.minCol[s], cMin);
+        if (tLo != SSG_NIL) { atomicMin(&tb.tMin[s], tLo); atomicMax(&tb.tMax1[s], tHi); }
+        if (lLo != SSG_NIL) { atomicMin(&tb.lMin[s], lLo); atomicMax(&tb.lMax1[s], lHi); }
+        if (anyTrim) tb.inTrim[s] = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_flags(StitchTables tb, int64_t len, int hasTop, int hasLeft, unsigned midT, unsigned midL,
+             int64_t top, int64_t bottom, int64_t left, int64_t right, unsigned char *flags,
+             unsigned *numbered)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    unsigned f = 0, num = 0;
+    if (s != 0 && tb.minRow[s] != SSG_NIL) {
+        f |= SSG_SEG_PRESENT;
+        // crossesMidline: min < mid and max >= mid (tiling.py:1303-1306)
+        if (hasTop && tb.tMin[s] < midT && tb.tMax1[s] > midT) f |= SSG_SEG_KEYTOP;
+        if (hasLeft && tb.lMin[s] < midL && tb.lMax1[s] > midL) f |= SSG_SEG_KEYLEFT;
+        if (tb.inTrim[s]) f |= SSG_SEG_INTRIM;
+        const int64_t segLeft = tb.minCol[s], segTop = tb.minRow[s];
+        if (!(f & (SSG_SEG_KEYTOP | SSG_SEG_KEYLEFT)) && segLeft >= left && segTop >= top &&
+            segLeft < right && segTop < bottom) {   // tiling.py:1264-1265
+            f |= SSG_SEG_NUMBERED;
+            num = 1;
+        }
+    }
+    flags[s] = (unsigned char)f;
+    numbered[s] = num;
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_ranks(const unsigned *__restrict__ numbered, const unsigned *__restrict__ excl, int64_t len,
+             unsigned *rank, unsigned long long *counters)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    rank[s] = numbered[s] ? excl[s] + 1u : 0u;
+    if (s == len - 1) counters[C_SCRATCH1] = (unsigned long long)excl[s] + numbered[s];
+}
+
+// (strip, segment, neighbour label) keys of the strip pixels of the crossing segments
+__global__ void __launch_bounds__(256)
+k_collect_pairs(const unsigned *__restrict__ tile, int64_t xsize, int64_t stripRows, int64_t stripCols,
+                const unsigned *__restrict__ B, int64_t bStride, const unsigned char *__restrict__ flags,
+                unsigned keyFlag, unsigned long long stripBit, unsigned long long *keys,
+                unsigned long long *counters)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    unsigned long long key = 0;
+    if (t < stripRows * stripCols) {
+        const int64_t r = t / stripCols, c = t % stripCols;
+        const unsigned s = tile[r * xsize + c];
+        if (s != 0 && (flags[s] & keyFlag)) {
+            hit = true;
+            key = stripBit | ((unsigned long long)s << 32) | (unsigned long long)B[r * bStride + c];
+        }
+    }
+    unsigned long long slot = warp_claim(&counters[C_SCRATCH2], hit);
+    if (hit) keys[slot] = key;
+}
+
+static int reserveTables(ssg_ctx *ctx, int64_t len, StitchTables &tb, unsigned **numbered,
+                         unsigned **excl, unsigned **rank, unsigned char **flags)
+{
+    const size_t n = (size_t)len;
+    SSG_TRY(ssg_reserve(ctx, ctx->stitch0, n * 7 * sizeof(unsigned)));
+    SSG_TRY(ssg_reserve(ctx, ctx->stitch1, n * 3 * sizeof(unsigned) + n));
+    unsigned *base = bufp<unsigned>(ctx->stitch0);
+    tb.minRow = base; tb.minCol = base + n; tb.tMin = base + 2 * n; tb.lMin = base + 3 * n;
+    tb.tMax1 = base + 4 * n; tb.lMax1 = base + 5 * n; tb.inTrim = base + 6 * n;
+    unsigned *b1 = bufp<unsigned>(ctx->stitch1);
+    *numbered = b1; *excl = b1 + n; *rank = b1 + 2 * n;
+    *flags = reinterpret_cast<unsigned char *>(b1 + 3 * n);
+    // the four "min" tables start at NIL, the rest at 0
+    SSG_CUDA(ctx, cudaMemsetAsync(base, 0xFF, n * 4 * sizeof(unsigned), ctx->stream));
+    SSG_CUDA(ctx, cudaMemsetAsync(base + 4 * n, 0, n * 3 * sizeof(unsigned), ctx->stream));
+    return SSG_OK;
+}
+
+extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
+                                      int64_t overlap, const uint32_t *topBDev, int64_t topBStride,
+                                      const uint32_t *leftBDev, int64_t leftBStride, int64_t top,
+                                      int64_t bottom, int64_t left, int64_t right, ssg_tile_tables *out)
+{
+    if (!ctx) return SSG_ERR_ARG;
+    ctx->err.clear();
+    SSG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!tileDev || !out || ysize <= 0 || xsize <= 0 || overlap < 0) SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument");
+    unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
+    const int64_t N = ysize * xsize;
+    memset(out, 0, sizeof(*out));
+
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_MAXLABEL, 0, sizeof(unsigned long long), ctx->stream));
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_tile_max<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, N, counters);
+    SSG_LAUNCHED(ctx);
+    SSG_TRY(ssg_fetch_counters(ctx));
+    const unsigned maxId = (unsigned)ctx->hostCounters[C_MAXLABEL];
+    const int64_t len = (int64_t)maxId + 1;
+
+    StitchTables tb;
+    unsigned *numbered, *excl, *rank;
+    unsigned char *flags;
+    SSG_TRY(reserveTables(ctx, len, tb, &numbered, &excl, &rank, &flags));
+    const int64_t topRows = topBDev ? (overlap < ysize ? overlap : ysize) : 0;
+    const int64_t leftCols = leftBDev ? (overlap < xsize ? overlap : xsize) : 0;
+    k_tile_extents<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, ysize, xsize, topRows, leftCols, top, bottom,
+                                                            left, right, tb);
+    SSG_LAUNCHED(ctx);
+    // mid = int(n / 2) of the strip's stitch axis (tiling.py:1297,1300)
+    k_tile_flags<<<gridFor(len, 256), 256, 0, ctx->stream>>>(tb, len, topBDev != nullptr, leftBDev != nullptr,
+                                                            (unsigned)(topRows / 2), (unsigned)(leftCols / 2), top,
+                                                            bottom, left, right, flags, numbered);
+    SSG_LAUNCHED(ctx);
+    size_t tmpBytes = 0;
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, numbered, excl, (int)len, ctx->stream));
+    SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, numbered, excl, (int)len, ctx->stream));
+    ctx->launches++;
+    k_tile_ranks<<<gridFor(len, 256), 256, 0, ctx->stream>>>(numbered, excl, len, rank, counters);
+    SSG_LAUNCHED(ctx);
+
+    // neighbour-label histograms of the crossing segments
+    const int64_t nTop = topRows * xsize, nLeft = ysize * leftCols;
+    uint32_t numPairs = 0;
+    if (nTop + nLeft > 0) {
+        SSG_TRY(ssg_reserve(ctx, ctx->stitch2, (size_t)(nTop + nLeft) * sizeof(unsigned long long)));
+        unsigned long long *keys = bufp<unsigned long long>(ctx->stitch2);
+        if (nTop > 0) {
+            k_collect_pairs<<<gridFor(nTop, 256), 256, 0, ctx->stream>>>(tileDev, xsize, topRows, xsize, topBDev, topBStride,
+                                                                      flags, SSG_SEG_KEYTOP, 0ull, keys, counters);
+            SSG_LAUNCHED(ctx);
+        }
+        if (nLeft > 0) {
+            k_collect_pairs<<<gridFor(nLeft, 256), 256, 0, ctx->stream>>>(tileDev, xsize, ysize, leftCols, leftBDev, leftBStride,
+                                                                       flags, SSG_SEG_KEYLEFT, SSG_PAIR_LEFT, keys, counters);
+            SSG_LAUNCHED(ctx);
+        }
+        SSG_TRY(ssg_fetch_counters(ctx));
+        const int64_t M = (int64_t)ctx->hostCounters[C_SCRATCH2];
+        if (M > 0) {
+            SSG_TRY(ssg_reserve(ctx, ctx->stitch3, (size_t)M * sizeof(unsigned long long)));
+            SSG_TRY(ssg_reserve(ctx, ctx->stitch4, (size_t)M * sizeof(unsigned long long)));
+            SSG_TRY(ssg_reserve(ctx, ctx->stitch5, (size_t)M * sizeof(unsigned)));
+            unsigned long long *sorted = bufp<unsigned long long>(ctx->stitch3);
+            unsigned long long *uniq = bufp<unsigned long long>(ctx->stitch4);
+            unsigned *cnts = bufp<unsigned>(ctx->stitch5);
+            SSG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keys, sorted, (int)M, 0, 64, ctx->stream));
+            SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+            SSG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->cubTemp.p, tmpBytes, keys, sorted, (int)M, 0, 64, ctx->stream));
+            ctx->launches++;
+            unsigned long long *dRuns = counters + C_SCRATCH3;
+            SSG_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(nullptr, tmpBytes, sorted, uniq, cnts, dRuns, (int)M, ctx->stream));
+            SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+            SSG_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(ctx->cubTemp.p, tmpBytes, sorted, uniq, cnts, dRuns, (int)M, ctx->stream));
+            ctx->launches++;
+            SSG_TRY(ssg_fetch_counters(ctx));
+            numPairs = (uint32_t)(ctx->hostCounters[C_SCRATCH3] & 0xffffffffu);
+        }
+    } else {
+        SSG_TRY(ssg_fetch_counters(ctx));
+    }
+    out->maxId = maxId;
+    out->countNew = (uint32_t)ctx->hostCounters[C_SCRATCH1];
+    out->numPairs = numPairs;
+    ctx->stitchLen = len;
+    ctx->stitchPairs = numPairs;
+    return SSG_OK;
+}
+
+extern "C" int ssg_tile_tables_fetch(ssg_ctx *ctx, uint32_t *rank, uint8_t *flags, uint64_t *pairKeys,
+                                     uint32_t *pairCounts)
+{
+    if (!ctx) return SSG_ERR_ARG;
+    ctx->err.clear();
+    SSG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->stitchLen;
+    if (n == 0) SSG_FAIL(ctx, SSG_ERR_STATE, "ssg_tile_tables_device has not been called");
+    unsigned *b1 = bufp<unsigned>(ctx->stitch1);
+    if (rank) SSG_CUDA(ctx, cudaMemcpyAsync(rank, b1 + 2 * n, n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags) SSG_CUDA(ctx, cudaMemcpyAsync(flags, b1 + 3 * n, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->stitchPairs > 0) {
+        if (pairKeys) SSG_CUDA(ctx, cudaMemcpyAsync(pairKeys, ctx->stitch4.p, (size_t)ctx->stitchPairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (pairCounts) SSG_CUDA(ctx, cudaMemcpyAsync(pairCounts, ctx->stitch5.p, (size_t)ctx->stitchPairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+
+// out = lut[tile] over the trimmed window (+ histogram of what was written)
+__global__ void __launch_bounds__(256)
+k_apply_lut_window(const unsigned *__restrict__ tile, int64_t xsize, const unsigned *__restrict__ lut,
+                   int64_t top, int64_t left, int64_t wRows, int64_t wCols, unsigned *out,
+                   int64_t outStride, unsigned long long *hist, int64_t histLen)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < wRows * wCols;
+    unsigned v = 0;
+    if (valid) {
+        const int64_t r = t / wCols, c = t % wCols;
+        v = __ldg(lut + tile[(r + top) * xsize + (c + left)]);
+        out[r * outStride + c] = v;
+    }
+    if (!hist) return;
+    const bool use = valid && (int64_t)v < histLen;
+    const unsigned active = __ballot_sync(0xffffffffu, use);
+    if (!use) return;
+    const unsigned peers = __match_any_sync(active, v);
+    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[v], (unsigned long long)__popc(peers));
+}
+
+extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
+                                    const uint32_t *lutHost, uint32_t maxId, int64_t top, int64_t bottom,
+                                    int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
+                                    uint64_t *histDev, int64_t histLen)
+{
+    if (!ctx) return SSG_ERR_ARG;
+    ctx->err.clear();
+    SSG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!tileDev || !lutHost || !outDev) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
+    if (top < 0 || left < 0 || bottom > ysize || right > xsize || top > bottom || left > right) SSG_FAIL(ctx, SSG_ERR_ARG, "bad window");
+    const size_t n = (size_t)maxId + 1;
+    SSG_TRY(ssg_reserve(ctx, ctx->lut, n * sizeof(unsigned)));
+    ctx->lutStage.assign(lutHost, lutHost + n);
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->lut.p, ctx->lutStage.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t wRows = bottom - top, wCols = right - left;
+    if (wRows * wCols > 0) {
+        k_apply_lut_window<<<gridFor(wRows * wCols, 256), 256, 0, ctx->stream>>>(
+            tileDev, xsize, bufp<unsigned>(ctx->lut), top, left, wRows, wCols, outDev, outStride,
+            reinterpret_cast<unsigned long long *>(histDev), histLen);
+        SSG_LAUNCHED(ctx);
+    }
+    return SSG_OK;
+}

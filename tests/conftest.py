@@ -15,11 +15,18 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     """GPU tests are skipped (not failed) when no device is visible, e.g. a plain
     `pytest tests` in the development container."""
+    have = False
     try:
-        import torch
-        have = torch.cuda.is_available()
+        # cheap probe through our own library; torch only if the library is not built, so that
+        # GPU tests on a GPU box fail loudly (instead of being skipped) when it is missing
+        from pyshepseg_b200 import _lib
+        have = _lib.load().ssg_device_count() > 0
     except Exception:
-        have = False
+        try:
+            import torch
+            have = torch.cuda.is_available()
+        except Exception:
+            have = False
     if have:
         return
     skip = pytest.mark.skip(reason='no CUDA device')
