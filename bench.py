@@ -1,0 +1,465 @@
+"""
+bench.py -- Mpixels/s of the full Shepherd segmentation (assign + clump + eliminate + stitch)
+on B200, next to the CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the hot path over one synthetic raster: the workload named by
+BASELINE.json configs[1], a Sentinel-2-like 10980 x 10980 x 4 uint16 raster segmented by
+doTiledShepherdSegmentation with tileSize=4096, overlapSize=1024 (2 x 2 tiles of 4096 and 7908
+pixels), numClusters=60, minSegmentSize=50, maxSpectralDiff='auto', four-connected, with given
+cluster centres (the k-means fit is host-side set-up, not part of the path).  Pixels counted are
+the unique pixels of the raster.
+
+Two numbers per run:
+  value  the tiled segmentation with the raster resident in HBM and the mosaic written to HBM
+         (pyshepseg_b200.tiling.TiledSegmenter over DeviceRaster / DeviceMosaicSink);
+  e2e    the same call with the raster in pinned HOST memory and the mosaic delivered to HOST
+         memory, copies inside the timed region (the public path of doTiledShepherdSegmentation
+         with two segmentation workers overlapping copies and kernels).
+
+With --gpus N (launched by torchrun, one rank per GPU) every rank segments its own scene of
+the same shape (weak scaling; tiles of different scenes are independent, so the data path has
+no collective); NCCL broadcasts the cluster centres from rank 0 and all-gathers every scene's
+segment count per step, from which each scene's global id base follows.
+
+--impl reference times the CPU restatement of the reference (oracle/, a plain C port of the
+numba / scikit-learn path, validated bit for bit against the reference) on the host cores, on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pyshepseg_b200 import synth  # noqa: E402
+
+WORKLOAD = {
+    'name': 's2like_10980x10980x4_u16_tiled',
+    'rows': 10980, 'cols': 10980, 'bands': 4, 'tileSize': 4096, 'overlapSize': 1024,
+    'numClusters': 60, 'minSegmentSize': 50, 'maxSpectralDiff': 'auto', 'fourConnected': True,
+}
+METRIC = 'Mpixels/sec full segmentation (assign+clump+eliminate+stitch), tiled 10980x10980x4 uint16'
+UNIT = 'Mpixel/s'
+
+# algorithmic bytes per pixel of the kernels:
+# what one launch must move at the very least, per pixel it processes
+def algorithmic_bytes_per_pixel(kernel, nB):
+    table = {
+        'k_assign': 2 * nB + 4,            # read the bands, write the int32 cluster
+        'k_ccl_local': 8,                  # read cluster, write root label
+        'k_ccl_flatten': 8,
+        'k_gather_ids': 8,
+        'k_single_decide': 8,              # read label + size of every pixel
+        'k_band_sums': 2 * nB + 4,         # read the bands and the label
+        'k_list_fill': 4,
+        'k_small_persistent': 2 * nB + 8,  # the "eliminate" figure: bands once, labels read + written
+        'k_apply_lut': 8,
+        'k_apply_lut_window': 8,
+        'k_tile_extents': 4,
+        'k_tile_max': 4,
+        'k_count_roots': 4,
+        'k_number_roots': 4,
+    }
+    return table.get(kernel)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return (json.load(open(path)).get('hbm_gbs', 6650.0), 'measured')
+    return (6650.0, 'fallback')
+
+
+class KM(object):
+    def __init__(self, centres):
+        self.cluster_centers_ = numpy.ascontiguousarray(centres, dtype=numpy.float64)
+
+
+def make_scene(wl, seed, out=None):
+    """The synthetic raster of one scene (cached on /tmp so the two arms share it)."""
+    cache = '/tmp/shepseg_bench_%s_seed%d.npy' % (wl['name'], seed)
+    shape = (wl['bands'], wl['rows'], wl['cols'])
+    if os.path.exists(cache):
+        try:
+            a = numpy.load(cache, mmap_mode='r')
+            if a.shape == shape:
+                if out is None:
+                    return numpy.array(a)
+                out[...] = a
+                return out
+        except Exception:
+            pass
+    img = synth.synth_tiled(wl['rows'], wl['cols'], wl['bands'], seed=seed, out=out)
+    try:
+        numpy.save(cache + '.tmp.npy', img)
+        os.replace(cache + '.tmp.npy', cache)
+    except Exception:
+        pass
+    return img
+
+
+def scene_centres(wl, img):
+    return synth.diagonal_centres(img, wl['numClusters'])
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+        'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
+                '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = []
+        smMax = None
+        reasons = set()
+        power = []
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smMax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for (name, val) in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                    'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(numpy.median(sm)) if sm else None, 'sm_max_mhz': smMax,
+            'reasons': sorted(reasons), 'samples': len(sm),
+            'power_w_max': max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# the CPU arm: the oracle port of the reference on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl, img, centres, threads, tile=4096):
+    """
+    One bounded sample of the workload on the CPU: `threads` tiles of tile x tile pixels cut
+    from the raster, one per thread, each through the oracle's doShepherdSegmentation (the
+    reference's numba stages are single threaded; using all cores means one tile per core,
+    BASELINE.md section 3).  Returns (pixels, seconds).
+    """
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from oracle import oracle
+    oracle.lib()
+    km = KM(centres)
+    step = max(1, (wl['rows'] - tile) // max(1, threads - 1)) if threads > 1 else 0
+    crops = []
+    for i in range(threads):
+        y = min(i * step, wl['rows'] - tile)
+        x = min((i * 977) % max(1, wl['cols'] - tile), wl['cols'] - tile)
+        crops.append(numpy.ascontiguousarray(img[:, y:y + tile, x:x + tile]))
+    done = [None] * threads
+
+    def work(i):
+        done[i] = oracle.doShepherdSegmentation(crops[i], minSegmentSize=wl['minSegmentSize'],
+            maxSpectralDiff=wl['maxSpectralDiff'], fourConnected=wl['fourConnected'], kmeansObj=km)
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.time()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.time() - t0
+    return (threads * tile * tile, dt)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 16)
+    tile = 2048 if args.quick else 4096
+    img = make_scene(wl, seed=1)
+    centres = scene_centres(wl, img)
+    for _ in range(args.warmup):
+        cpu_reference_sample(wl, img, centres, threads, tile=min(tile, 1024))
+    pix = 0
+    secs = 0.0
+    for _ in range(args.steps):
+        (p, s) = cpu_reference_sample(wl, img, centres, threads, tile=tile)
+        pix += p
+        secs += s
+    value = pix / secs / 1e6
+    sample = '%d tiles of %dx%dx%d cut from the workload raster per step, one per thread' % (
+        threads, tile, tile, wl['bands'])
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16',
+        'data': 'synthetic', 'config': workload_config(wl, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, gpus):
+    return {'workload': wl['name'], 'raster': [wl['bands'], wl['rows'], wl['cols']], 'dtype': 'uint16',
+        'tileSize': wl['tileSize'], 'overlapSize': wl['overlapSize'], 'tiles': '2x2 (4096, 7908)',
+        'numClusters': wl['numClusters'], 'minSegmentSize': wl['minSegmentSize'],
+        'maxSpectralDiff': wl['maxSpectralDiff'], 'fourConnected': wl['fourConnected'],
+        'scenes': gpus, 'parallelism': 'one scene per GPU' if gpus > 1 else 'single GPU',
+        'l2_policy': 'inputs larger than L2 (964 MB raster, 482 MB mosaic per scene)'}
+
+
+# ---------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    from pyshepseg_b200 import _lib, shepseg, tiling, rasterfile, timinghooks
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('--gpus %d needs torchrun with %d ranks' % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    # ---- set-up (untimed): scene in pinned host memory, centres from rank 0 over NCCL ----
+    (nB, nR, nC) = (wl['bands'], wl['rows'], wl['cols'])
+    pinnedImg = _lib.PinnedArray((nB, nR, nC), numpy.uint16)
+    img = make_scene(wl, seed=1 + rank, out=pinnedImg.array)
+    if rank == 0:
+        centres = scene_centres(wl, img)
+    else:
+        centres = numpy.zeros((wl['numClusters'], nB))
+    if dist is not None:
+        t = torch.from_numpy(centres).cuda()
+        dist.broadcast(t, 0)
+        centres = t.cpu().numpy()
+    centres = numpy.ascontiguousarray(centres, dtype=numpy.float64)
+    km = KM(centres)
+    msd = shepseg.autoMaxSpectralDiff(km, wl['maxSpectralDiff'], 50)
+    thr = shepseg.spectralThreshold(msd)
+    tileInfo = tiling.getTilesForFile((nC, nR), wl['tileSize'], wl['overlapSize'])
+    pinnedOut = _lib.PinnedArray((nR, nC), numpy.uint32)
+
+    state = tiling.gpuState(local)
+    ctx0 = state.slot(0).ctx
+    devImg = ctx0.dev_alloc(img.nbytes)
+    ctx0.call('ssg_memcpy_h2d', devImg, _lib.ptr(img), img.nbytes)
+    ctx0.synchronize()
+    devMosaic = ctx0.dev_alloc(nR * nC * 4)
+
+    def step_resident(profile=False):
+        cfg = tiling.SegmentationConcurrencyConfig(devices=[local])
+        seg = tiling.TiledSegmenter(tiling.DeviceRaster(devImg, nB, nR, nC, numpy.uint16), range(1, nB + 1),
+            tileInfo, wl['overlapSize'], centres, None, wl['fourConnected'], wl['minSegmentSize'], thr,
+            False, cfg, timinghooks.Timers(), profile=profile)
+        (maxSegId, hist) = seg.run(tiling.DeviceMosaicSink(devMosaic, nC, nR))
+        return (seg, maxSegId)
+
+    def step_e2e():
+        cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=2,
+            devices=[local], tileCompletionTimeout=600)
+        sink = rasterfile.MemorySink.__new__(rasterfile.MemorySink)
+        sink.array = pinnedOut.array
+        sink.metadata = {}
+        sink.nodata = None
+        sink.hist = None
+        seg = tiling.TiledSegmenter(rasterfile.MemoryRaster(img), range(1, nB + 1), tileInfo,
+            wl['overlapSize'], centres, None, wl['fourConnected'], wl['minSegmentSize'], thr, False, cfg,
+            timinghooks.Timers())
+        (maxSegId, hist) = seg.run(sink)
+        return (seg, maxSegId)
+
+    def exchange_ids(maxSegId):
+        """per-scene id base = exclusive scan of the scenes' segment counts (NCCL all-gather)"""
+        if dist is None:
+            return 0
+        mine = torch.tensor([maxSegId], dtype=torch.int64, device='cuda')
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        return int(sum(int(v.item()) for v in allv[:rank]))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(stepFn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = stepFn()
+            exchange_ids(last[1])
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return (ms, last)
+
+    # ---- warm-up -----------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+        step_e2e()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: resident (value) with per-kernel events, then host-to-host (e2e) ------------------
+    launches0 = sum(s.ctx.launch_count() for s in state.slots)
+    kernelAgg = {}
+
+    def resident_profiled():
+        r = step_resident(profile=True)
+        for (k, v) in r[0].kernelMs.items():
+            ent = kernelAgg.setdefault(k, [0, 0.0])
+            ent[0] += v[0]
+            ent[1] += v[1]
+        return r
+    (msResident, lastRes) = timed(resident_profiled, args.steps)
+    launchesResident = sum(s.ctx.launch_count() for s in state.slots) - launches0
+    (msE2E, lastE2E) = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    pixelsPerStep = nR * nC * world
+    value = pixelsPerStep * args.steps / (msResident / 1e3) / 1e6
+    e2eValue = pixelsPerStep * args.steps / (msE2E / 1e3) / 1e6
+    segE2E = lastE2E[0]
+
+    # the e2e mosaic must be the resident mosaic (same labels, one went over PCIe)
+    check = numpy.empty((64, nC), dtype=numpy.uint32)
+    ctx0.call('ssg_memcpy_d2h', _lib.ptr(check), devMosaic + (nR // 2) * nC * 4, check.nbytes)
+    sameMosaic = bool(numpy.array_equal(check, pinnedOut.array[nR // 2:nR // 2 + 64]))
+
+    if rank == 0:
+        (peak, peakKind) = measured_peaks()
+        # roofline of the dominant kernel, from the events recorded around every launch
+        dom = max(kernelAgg.items(), key=lambda kv: kv[1][1]) if kernelAgg else (None, [0, 0.0])
+        (domName, (domCount, domMs)) = dom
+        tilePixels = sum(t[2] * t[3] for t in tileInfo.tiles.values())
+        bpp = algorithmic_bytes_per_pixel(domName, nB)
+        roof = {'bound': 'hbm', 'kernel': domName, 'achieved': None, 'peak': peak, 'unit': 'GB/s',
+            'frac': None, 'traffic': None, 'peak_source': peakKind}
+        if bpp is not None and domCount > 0 and domMs > 0:
+            # one launch per tile: algorithmic bytes per launch = bytes/pixel x mean tile pixels
+            launchesPerStep = domCount / args.steps
+            bytesPerLaunch = bpp * tilePixels / max(1.0, launchesPerStep)
+            avgMs = domMs / domCount
+            roof['achieved'] = bytesPerLaunch / (avgMs / 1e3) / 1e9
+            roof['frac'] = roof['achieved'] / peak
+            roof['bytes_per_pixel'] = bpp
+            roof['avg_launch_ms'] = avgMs
+            roof['launches_per_step'] = launchesPerStep
+            roof['share_of_step'] = domMs / msResident
+        kernels = dict((k, {'launches': v[0], 'ms': round(v[1], 3)}) for (k, v) in sorted(kernelAgg.items(),
+            key=lambda kv: -kv[1][1])[:12])
+        # secondary rooflines of the two bandwidth kernels the north star names
+        extra = {}
+        for name in ('k_assign', 'k_ccl_local'):
+            if name in kernelAgg and kernelAgg[name][1] > 0:
+                b = algorithmic_bytes_per_pixel(name, nB)
+                gbs = b * tilePixels * args.steps / (kernelAgg[name][1] / 1e3) / 1e9
+                extra[name] = {'achieved': gbs, 'frac': gbs / peak, 'bytes_per_pixel': b}
+
+        cpu = None
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            threads = min(os.cpu_count() or 1, 16)
+            tile = 2048 if args.quick else 4096
+            (p, s) = cpu_reference_sample(wl, img, centres, threads, tile=tile)
+            cpu = {'value': p / s / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                'sample': '%d tiles of %dx%dx%d cut from the workload raster, one per thread (%.1f s)' % (
+                    threads, tile, tile, nB, s)}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': msResident / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16', 'data': 'synthetic',
+            'config': workload_config(wl, args.gpus),
+            'e2e': {'value': e2eValue, 'unit': UNIT, 'ms_per_step': msE2E / args.steps,
+                'h2d_bytes_per_step': int(segE2E.h2dBytes), 'd2h_bytes_per_step': int(segE2E.d2hBytes),
+                'workers': 2, 'same_labels_as_resident': sameMosaic},
+            'gpu_launches': int(launchesResident),
+            'roofline': roof, 'roofline_other': extra, 'kernels': kernels,
+            'cpu_baseline': cpu, 'clocks': clocks,
+            'segments_per_scene': int(lastRes[1]),
+            'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastRes[0].stageMs.items()),
+        }
+        print(json.dumps(line), flush=True)
+
+    ctx0.dev_free(devImg)
+    ctx0.dev_free(devMosaic)
+    tiling.releaseGpuState()
+    pinnedImg.free()
+    pinnedOut.free()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--quick', action='store_true', help='2048-pixel raster and tiles (smoke runs only)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = dict(WORKLOAD)
+    if args.quick:
+        wl.update({'name': 'quick_2700x2700x4', 'rows': 2700, 'cols': 2700, 'tileSize': 1024, 'overlapSize': 256})
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

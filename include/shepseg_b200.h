@@ -130,6 +130,12 @@ int ssg_segment_tile(ssg_ctx *ctx, const void *imgHost, const ssg_tile_params *p
  * keep them in the context; otherwise a device pointer to nRows*nCols uint32). */
 int ssg_segment_tile_device(ssg_ctx *ctx, const void *imgDev, const ssg_tile_params *prm,
                             uint32_t *segOutDev, ssg_tile_result *res);
+/* stage a host image in the context's device image buffer (asynchronous on the context's
+ * stream when imgHost is pinned); ssg_staged_image returns that device pointer, to be passed
+ * to ssg_segment_tile_device together with a per-tile device label buffer */
+int ssg_upload_image(ssg_ctx *ctx, const void *imgHost, int dtype, int nBands, int64_t nRows,
+                     int64_t nCols);
+void *ssg_staged_image(ssg_ctx *ctx);
 /* copy the resident labels of the last tile to host memory */
 int ssg_download_labels(ssg_ctx *ctx, uint32_t *segOutHost);
 /* device pointer of the resident labels of the last tile (owned by the context) */
@@ -208,6 +214,12 @@ int ssg_memcpy2d_d2h(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, si
 int ssg_memcpy2d_h2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch,
                      size_t widthBytes, size_t rows);
 int ssg_memset_d(ssg_ctx *ctx, void *dst, int value, size_t bytes);
+
+/* per-kernel device timing: while enabled every kernel launch is bracketed by two CUDA
+ * events on the context's stream; ssg_profile_fetch writes "name count total_ms" lines for
+ * the launches since the last fetch into buf (NUL terminated) and resets the records */
+int ssg_profile_enable(ssg_ctx *ctx, int on);
+int ssg_profile_fetch(ssg_ctx *ctx, char *buf, size_t cap);
 
 /* number of kernels this library has launched on the context since creation */
 uint64_t ssg_launch_count(const ssg_ctx *ctx);

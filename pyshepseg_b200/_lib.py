@@ -5,6 +5,7 @@ There is no CPU fallback: importing this module without the built library raises
 creating a Context without a CUDA device raises.  The library is built in-tree by
 `__graft_entry__.build()` (or `make -C pyshepseg_b200/csrc`).
 """
+import atexit
 import ctypes
 import os
 import threading
@@ -76,6 +77,8 @@ SIGNATURES = {
         _c.POINTER(_i64)]),
     'ssg_segment_tile': (_i, [_vp, _vp, _c.POINTER(TileParams), _vp, _c.POINTER(TileResult)]),
     'ssg_segment_tile_device': (_i, [_vp, _vp, _c.POINTER(TileParams), _vp, _c.POINTER(TileResult)]),
+    'ssg_upload_image': (_i, [_vp, _vp, _i, _i, _i64, _i64]),
+    'ssg_staged_image': (_vp, [_vp]),
     'ssg_download_labels': (_i, [_vp, _vp]),
     'ssg_resident_labels': (_vp, [_vp]),
     'ssg_tile_tables_device': (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64,
@@ -93,6 +96,8 @@ SIGNATURES = {
     'ssg_memcpy2d_h2d': (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     'ssg_memset_d': (_i, [_vp, _vp, _i, _sz]),
     'ssg_launch_count': (_c.c_uint64, [_vp]),
+    'ssg_profile_enable': (_i, [_vp, _i]),
+    'ssg_profile_fetch': (_i, [_vp, _c.c_char_p, _sz]),
 }
 
 _lib = None
@@ -227,6 +232,16 @@ class Context(object):
 
 _defaultCtx = {}
 _defaultLock = threading.Lock()
+
+
+def _closeDefaultContexts():
+    with _defaultLock:
+        for ctx in _defaultCtx.values():
+            ctx.close()
+        _defaultCtx.clear()
+
+
+atexit.register(_closeDefaultContexts)
 
 
 def default_context(device=0):

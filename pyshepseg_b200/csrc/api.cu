@@ -69,6 +69,46 @@ uint64_t ssg_launch_count(const ssg_ctx *ctx) { return ctx ? ctx->launches : 0; 
     (ctx)->err.clear();                                                 \
     SSG_CUDA(ctx, cudaSetDevice((ctx)->device))
 
+int ssg_profile_enable(ssg_ctx *ctx, int on)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->profiling = on != 0;
+    ctx->profUsed = 0;
+    ctx->profOpen = false;
+    return SSG_OK;
+}
+
+// "name count total_ms\n" per kernel, since the last fetch / enable
+int ssg_profile_fetch(ssg_ctx *ctx, char *buf, size_t cap)
+{
+    CTX_ENTER(ctx);
+    if (!buf || cap == 0) SSG_FAIL(ctx, SSG_ERR_ARG, "null buffer");
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<double> total(ctx->profNames.size(), 0.0);
+    std::vector<long long> count(ctx->profNames.size(), 0);
+    for (size_t r = 0; r < ctx->profUsed; r++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->profEvents[2 * r], ctx->profEvents[2 * r + 1]) == cudaSuccess) {
+            total[ctx->profRecName[r]] += ms;
+            count[ctx->profRecName[r]]++;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    std::string out;
+    char line[256];
+    for (size_t i = 0; i < ctx->profNames.size(); i++) {
+        if (!count[i]) continue;
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", ctx->profNames[i].c_str(), count[i], total[i]);
+        out += line;
+    }
+    ctx->profUsed = 0;
+    if (out.size() + 1 > cap) SSG_FAIL(ctx, SSG_ERR_ARG, "profile buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return SSG_OK;
+}
+
 int ssg_ctx_synchronize(ssg_ctx *ctx)
 {
     CTX_ENTER(ctx);
@@ -317,6 +357,7 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     // (oldMaxSegId - seg.max() after its order-preserving relabel, shepseg.py:226-227)
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, sizeof(unsigned long long), ctx->stream));
     if (numClumps > 0) {
+        SSG_PROF_BEGIN(ctx, "k_count_zero_sizes");
         k_count_zero_sizes<<<gridFor(numClumps, 256), 256, 0, ctx->stream>>>(segSize, 1, len, counters + C_SCRATCH1);
         SSG_LAUNCHED(ctx);
     }
@@ -393,6 +434,15 @@ int ssg_segment_tile(ssg_ctx *ctx, const void *imgHost, const ssg_tile_params *p
     }
     return SSG_OK;
 }
+
+int ssg_upload_image(ssg_ctx *ctx, const void *imgHost, int dtype, int nBands, int64_t nRows, int64_t nCols)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(check_image_args(ctx, imgHost, dtype, nBands, nRows, nCols));
+    return upload_image(ctx, imgHost, dtype, nBands, nRows * nCols);
+}
+
+void *ssg_staged_image(ssg_ctx *ctx) { return ctx ? ctx->img.p : nullptr; }
 
 int ssg_download_labels(ssg_ctx *ctx, uint32_t *segOutHost)
 {

@@ -197,6 +197,7 @@ static int launch_assign(ssg_ctx *ctx, const void *img, int64_t N, const double 
     int64_t cap = (int64_t)ctx->numSMs * 64;   // grid-stride beyond this; keeps the centre prologue amortised
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    SSG_PROF_BEGIN(ctx, "k_assign");
     kern<<<(unsigned)blocks, 256, smem, ctx->stream>>>(reinterpret_cast<const T *>(img), N, centresDev,
                                                       k, hasNull, nullVal, bnd, out);
     SSG_LAUNCHED(ctx);

@@ -275,13 +275,16 @@ static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t N, un
     unsigned *blockCnt = bufp<unsigned>(ctx->blockCnt);
     unsigned *blockOff = blockCnt + nBlocks;
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_ROOTS, 0, sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_count_roots");
     k_count_roots<<<(unsigned)nBlocks, 256, 0, ctx->stream>>>(label, N, blockCnt, counters);
     SSG_LAUNCHED(ctx);
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, blockCnt, blockOff, (int)nBlocks, ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, blockCnt, blockOff, (int)nBlocks, ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
+    SSG_PROF_BEGIN(ctx, "k_number_roots");
     k_number_roots<<<(unsigned)nBlocks, 256, 0, ctx->stream>>>(label, N, blockOff, clumpId, seg);
     SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
@@ -289,6 +292,7 @@ static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t N, un
     const size_t len = (size_t)clumpId + *numRoots;
     SSG_TRY(ssg_reserve(ctx, ctx->segSize, len * sizeof(unsigned)));
     SSG_CUDA(ctx, cudaMemsetAsync(ctx->segSize.p, 0, len * sizeof(unsigned), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_gather_ids");
     k_gather_ids<<<gridFor(N, 256), 256, 0, ctx->stream>>>(label, N, seg, bufp<unsigned>(ctx->segSize));
     SSG_LAUNCHED(ctx);
     return SSG_OK;
@@ -372,6 +376,7 @@ static int split_oversized(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int6
     const int64_t N = nRows * nCols;
     SSG_TRY(ssg_reserve(ctx, ctx->flags, (size_t)sizeLen));
     unsigned char *flag = bufp<unsigned char>(ctx->flags);
+    SSG_PROF_BEGIN(ctx, "k_flag_oversized");
     k_flag_oversized<<<gridFor(sizeLen, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), sizeLen, flag);
     SSG_LAUNCHED(ctx);
     // pixels of the flagged regions, grouped by region, raster order inside each region
@@ -380,11 +385,13 @@ static int split_oversized(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int6
     unsigned numRuns = 0;
     SSG_TRY(ssgk_group_pixels(ctx, seg, N, flag, &pixSorted, nullptr, &runStart, &M, &numRuns));
     if (M == 0) return SSG_OK;
+    SSG_PROF_BEGIN(ctx, "k_mark_unvisited");
     k_mark_unvisited<<<gridFor(M, 256), 256, 0, ctx->stream>>>(pixSorted, M, label);
     SSG_LAUNCHED(ctx);
     const unsigned stackCap = SSG_MAX_CLUMP_SIZE + 32;
     SSG_TRY(ssg_reserve(ctx, ctx->emuStack, (size_t)numRuns * stackCap * sizeof(unsigned)));
     const unsigned warpsPerBlock = 4;
+    SSG_PROF_BEGIN(ctx, "k_capped_fill");
     k_capped_fill<<<(numRuns + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, 0, ctx->stream>>>(
         img, nRows, nCols, four, pixSorted, runStart, numRuns, M, label, bufp<unsigned>(ctx->emuStack), stackCap);
     SSG_LAUNCHED(ctx);
@@ -406,13 +413,16 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
 
     dim3 grid((unsigned)((nCols + CCL_TW - 1) / CCL_TW), (unsigned)((nRows + CCL_TH - 1) / CCL_TH));
+    SSG_PROF_BEGIN(ctx, "k_ccl_local");
     k_ccl_local<<<grid, CCL_THREADS, 0, ctx->stream>>>(clusterDev, nRows, nCols, ignoreVal, four, label);
     SSG_LAUNCHED(ctx);
     const int64_t nHB = (nRows - 1) / CCL_TH, nVB = (nCols - 1) / CCL_TW;
     const int64_t nBorder = nHB * nCols + nVB * nRows;
     if (nBorder > 0) {
+        SSG_PROF_BEGIN(ctx, "k_ccl_border");
         k_ccl_border<<<gridFor(nBorder, 256), 256, 0, ctx->stream>>>(clusterDev, nRows, nCols, ignoreVal, four, label, nHB, nVB);
         SSG_LAUNCHED(ctx);
+        SSG_PROF_BEGIN(ctx, "k_ccl_flatten");
         k_ccl_flatten<<<gridFor(N, 256), 256, 0, ctx->stream>>>(label, N);
         SSG_LAUNCHED(ctx);
     }
@@ -420,6 +430,7 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
     SSG_TRY(number_from_labels(ctx, label, N, clumpId, segDev, &numRoots));
     // oversized regions / single-pixel clumps
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_OVERSIZED, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_count_oversized");
     k_count_oversized<<<gridFor(numRoots, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), (int64_t)clumpId,
                                                                        (int64_t)clumpId + numRoots, counters);
     SSG_LAUNCHED(ctx);
@@ -430,6 +441,7 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
         SSG_TRY(split_oversized(ctx, clusterDev, nRows, nCols, four, label, segDev, (int64_t)clumpId + numRoots));
         SSG_TRY(number_from_labels(ctx, label, N, clumpId, segDev, &numRoots));
         SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_OVERSIZED, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        SSG_PROF_BEGIN(ctx, "k_count_oversized");
         k_count_oversized<<<gridFor(numRoots, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), (int64_t)clumpId,
                                                                            (int64_t)clumpId + numRoots, counters);
         SSG_LAUNCHED(ctx);
@@ -457,6 +469,7 @@ int ssgk_seg_size(ssg_ctx *ctx, const uint32_t *segDev, int64_t N, uint32_t *siz
 {
     SSG_CUDA(ctx, cudaMemsetAsync(sizeDev, 0, (size_t)len * sizeof(unsigned), ctx->stream));
     if (N == 0) return SSG_OK;
+    SSG_PROF_BEGIN(ctx, "k_seg_size");
     k_seg_size<<<gridFor(N, 256), 256, 0, ctx->stream>>>(segDev, N, sizeDev, len);
     SSG_LAUNCHED(ctx);
     return SSG_OK;

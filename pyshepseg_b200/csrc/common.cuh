@@ -49,6 +49,14 @@ struct ssg_ctx {
     uint64_t *hostCounters = nullptr;   // pinned mirror of `counters`
     cudaEvent_t ev[8] = {};
 
+    // optional per-kernel timing (ssg_profile_enable): every launch bracketed by two events
+    bool profiling = false;
+    std::vector<std::string> profNames;
+    std::vector<int> profRecName;
+    std::vector<cudaEvent_t> profEvents;   // 2 per record
+    size_t profUsed = 0;                   // records in use
+    bool profOpen = false;
+
     // stitch tables of the last ssg_tile_tables_device call
     int64_t stitchLen = 0;
     uint32_t stitchPairs = 0;
@@ -108,10 +116,40 @@ enum Counter {
         if (_rc != SSG_OK) return _rc;                                  \
     } while (0)
 
+// per-kernel timing: SSG_PROF_BEGIN before a launch, SSG_LAUNCHED after it
+static inline void ssg_prof_begin(ssg_ctx *ctx, const char *name)
+{
+    if (!ctx->profiling) return;
+    int id = -1;
+    for (size_t i = 0; i < ctx->profNames.size(); i++)
+        if (ctx->profNames[i] == name) { id = (int)i; break; }
+    if (id < 0) { ctx->profNames.push_back(name); id = (int)ctx->profNames.size() - 1; }
+    if (ctx->profEvents.size() < 2 * (ctx->profUsed + 1)) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ctx->profEvents.push_back(a);
+        ctx->profEvents.push_back(b);
+    }
+    if (ctx->profRecName.size() <= ctx->profUsed) ctx->profRecName.push_back(id);
+    else ctx->profRecName[ctx->profUsed] = id;
+    cudaEventRecord(ctx->profEvents[2 * ctx->profUsed], ctx->stream);
+    ctx->profOpen = true;
+}
+static inline void ssg_prof_end(ssg_ctx *ctx)
+{
+    if (!ctx->profOpen) return;
+    cudaEventRecord(ctx->profEvents[2 * ctx->profUsed + 1], ctx->stream);
+    ctx->profUsed++;
+    ctx->profOpen = false;
+}
+#define SSG_PROF_BEGIN(ctx, name) ssg_prof_begin(ctx, name)
+
 // check the launch that has just been issued
 #define SSG_LAUNCHED(ctx)                                               \
     do {                                                                \
         (ctx)->launches++;                                              \
+        ssg_prof_end(ctx);                                              \
         SSG_CUDA(ctx, cudaGetLastError());                              \
     } while (0)
 

@@ -135,6 +135,7 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
     if (N == 0) return SSG_OK;
     // how many single-pixel segments are there (the lone null pixel counts, shepseg.py:652)
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_SINGLES, 0, sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_count_size_eq");
     k_count_size_eq<<<gridFor(len, 256), 256, 0, ctx->stream>>>(segSize, 0, len, 1u, counters + C_NUM_SINGLES);
     SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
@@ -152,6 +153,7 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
     unsigned *candOut = candA;
     while (true) {
         SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_MOVES, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        SSG_PROF_BEGIN(ctx, "k_single_decide");
         k_single_decide<T><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize, four,
                                                                        candIn, nIn, movePix, moveSeg, candOut, counters);
         SSG_LAUNCHED(ctx);
@@ -160,6 +162,7 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
         const int64_t nLeft = (int64_t)ctx->hostCounters[C_NUM_LEFT];
         (*numRounds)++;
         if (nMoves == 0) break;   // the reference's last, empty round (shepseg.py:610)
+        SSG_PROF_BEGIN(ctx, "k_single_apply");
         k_single_apply<<<gridFor(nMoves, 256), 256, 0, ctx->stream>>>(movePix, moveSeg, nMoves, seg, segSize);
         SSG_LAUNCHED(ctx);
         *numMoved += nMoves;
@@ -230,17 +233,21 @@ int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *size
     if (len <= 0) return SSG_OK;
     SSG_TRY(ssg_reserve(ctx, ctx->lut, (size_t)len * 2 * sizeof(unsigned)));
     unsigned *flag = bufp<unsigned>(ctx->lut), *lut = flag + len;
+    SSG_PROF_BEGIN(ctx, "k_zero_flags");
     k_zero_flags<<<gridFor(len, 256), 256, 0, ctx->stream>>>(sizeDev, len, minSegId, flag);
     SSG_LAUNCHED(ctx);
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, flag, flag, (int)len, ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, flag, flag, (int)len, ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_ALIVE, 0, sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_make_lut");
     k_make_lut<<<gridFor(len, 256), 256, 0, ctx->stream>>>(flag, sizeDev, len, minSegId, lut, counters);
     SSG_LAUNCHED(ctx);
     if (N > 0) {
+        SSG_PROF_BEGIN(ctx, "k_apply_lut");
         k_apply_lut<<<gridFor((N + 3) / 4, 256), 256, 0, ctx->stream>>>(segDev, N, lut);
         SSG_LAUNCHED(ctx);
     }
@@ -329,10 +336,12 @@ static int build_spectra_t(ssg_ctx *ctx, const T *img, int nB, int64_t N, const 
     unsigned char *bigFlag = bufp<unsigned char>(ctx->flags);
     SSG_CUDA(ctx, cudaMemsetAsync(isum, 0, n * sizeof(unsigned long long), ctx->stream));
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_BIGSUM, 0, sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_band_sums");
     k_band_sums<T><<<gridFor(N, 256), 256, 0, ctx->stream>>>(img, nB, N, seg, isum);
     SSG_LAUNCHED(ctx);
     constexpr bool isSigned = std::is_signed<T>::value;
     const unsigned maxAbs = sizeof(T) == 1 ? 255u : 32768u;
+    SSG_PROF_BEGIN(ctx, "k_finalize_sums");
     k_finalize_sums<isSigned><<<gridFor(len, 256), 256, 0, ctx->stream>>>(isum, segSize, nB, len, maxAbs, fsum, bigFlag, counters);
     SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
@@ -342,6 +351,7 @@ static int build_spectra_t(ssg_ctx *ctx, const T *img, int nB, int64_t N, const 
         unsigned numRuns = 0;
         SSG_TRY(ssgk_group_pixels(ctx, seg, N, bigFlag, &pixSorted, &keysSorted, &runStart, &M, &numRuns));
         if (M > 0) {
+            SSG_PROF_BEGIN(ctx, "k_ordered_sums");
             k_ordered_sums<T><<<gridFor((int64_t)numRuns * nB, 128), 128, 0, ctx->stream>>>(
                 img, nB, N, pixSorted, keysSorted, runStart, numRuns, M, fsum);
             SSG_LAUNCHED(ctx);
@@ -662,8 +672,9 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses)
         if (perSM > 4) perSM = 4;
         dim3 grid((unsigned)(ctx->numSMs * perSM)), block(256);
         void *args[] = {&st};
+        SSG_PROF_BEGIN(ctx, "k_small_persistent");
         SSG_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_small_persistent<NBMAX>, grid, block, args, 0, ctx->stream));
-        ctx->launches++;
+        SSG_LAUNCHED(ctx);
         SSG_TRY(ssg_fetch_counters(ctx));
         *numPasses = (uint32_t)ctx->hostCounters[C_NUM_PASSES];
         return SSG_OK;
@@ -677,6 +688,7 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses)
         while (true) {
             SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_CAND0 + par, 0, sizeof(unsigned long long), ctx->stream));
             SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_TARGETS0 + par, 0, sizeof(unsigned long long), ctx->stream));
+            SSG_PROF_BEGIN(ctx, "k_phase");
             k_phase<NBMAX><<<grid, 256, 0, ctx->stream>>>(st, 0, (unsigned)t, par);
             SSG_LAUNCHED(ctx);
             SSG_TRY(ssg_fetch_counters(ctx));
@@ -684,6 +696,7 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses)
             if (count == prev || np >= 10 || count == 0) break;
             prev = count;
             for (int ph = 1; ph <= 3; ph++) {
+                SSG_PROF_BEGIN(ctx, "k_phase");
                 k_phase<NBMAX><<<grid, 256, 0, ctx->stream>>>(st, ph, (unsigned)t, par);
                 SSG_LAUNCHED(ctx);
             }
@@ -713,13 +726,15 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     // chunk offsets: exclusive scan of the listed sizes, len+1 entries
     SSG_TRY(ssg_reserve(ctx, ctx->listOff, (size_t)(len + 1) * sizeof(unsigned)));
     unsigned *off = bufp<unsigned>(ctx->listOff);
+    SSG_PROF_BEGIN(ctx, "k_list_counts");
     k_list_counts<<<gridFor(len + 1, 256), 256, 0, ctx->stream>>>(segSize, len, (unsigned)minSegSize, off);
     SSG_LAUNCHED(ctx);
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, off, off, (int)(len + 1), ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, off, off, (int)(len + 1), ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
 
     const size_t tbl = (size_t)len * sizeof(unsigned);
     SSG_TRY(ssg_reserve(ctx, ctx->aux0, (size_t)N * sizeof(unsigned)));   // pixel array (<= N entries)
@@ -733,8 +748,10 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     unsigned *pix = bufp<unsigned>(ctx->aux0);
     unsigned *fill = bufp<unsigned>(ctx->candList);   // free until the passes start
     SSG_CUDA(ctx, cudaMemsetAsync(fill, 0, tbl, ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_list_fill");
     k_list_fill<<<gridFor(N, 256), 256, 0, ctx->stream>>>(seg, N, off, fill, pix);
     SSG_LAUNCHED(ctx);
+    SSG_PROF_BEGIN(ctx, "k_list_sort");
     k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(off, len, pix, bufp<unsigned>(ctx->nextChunk),
                                                            bufp<unsigned>(ctx->tailChunk), bufp<unsigned>(ctx->mergeTo),
                                                            bufp<unsigned>(ctx->pendHead));

@@ -44,8 +44,9 @@ int ssgk_group_pixels(ssg_ctx *ctx, const unsigned *segDev, int64_t N, const uns
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceSelect::If(nullptr, tmpBytes, cnt, pix, dNum, (int)N, pred, ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceSelect_If");
     SSG_CUDA(ctx, cub::DeviceSelect::If(ctx->cubTemp.p, tmpBytes, cnt, pix, dNum, (int)N, pred, ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
     const int64_t M = (int64_t)(ctx->hostCounters[C_SCRATCH0] & 0xffffffffu);
     if (M == 0) return SSG_OK;
@@ -55,19 +56,22 @@ int ssgk_group_pixels(ssg_ctx *ctx, const unsigned *segDev, int64_t N, const uns
     SSG_TRY(ssg_reserve(ctx, ctx->sortVals1, (size_t)M * sizeof(unsigned)));
     unsigned *keys0 = bufp<unsigned>(ctx->sortKeys0), *keys1 = bufp<unsigned>(ctx->sortKeys1);
     unsigned *pixSorted = bufp<unsigned>(ctx->sortVals1);
+    SSG_PROF_BEGIN(ctx, "k_fetch_keys");
     k_fetch_keys<<<gridFor(M, 256), 256, 0, ctx->stream>>>(pix, M, segDev, keys0);
     SSG_LAUNCHED(ctx);
     // LSD radix sort is stable: raster order survives inside each segment
     SSG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys0, keys1, pix, pixSorted, (int)M, 0, 32, ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceRadixSort_SortPairs");
     SSG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->cubTemp.p, tmpBytes, keys0, keys1, pix, pixSorted, (int)M, 0, 32, ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
     unsigned *runStart = keys0;   // keys0 is free again; at most M runs
     IsRunStart rs{keys1};
     SSG_CUDA(ctx, cub::DeviceSelect::If(nullptr, tmpBytes, cnt, runStart, dNum, (int)M, rs, ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceSelect_If");
     SSG_CUDA(ctx, cub::DeviceSelect::If(ctx->cubTemp.p, tmpBytes, cnt, runStart, dNum, (int)M, rs, ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
     *numRunsOut = (unsigned)(ctx->hostCounters[C_SCRATCH0] & 0xffffffffu);
     *MOut = M;

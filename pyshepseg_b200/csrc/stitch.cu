@@ -157,6 +157,7 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
 
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_MAXLABEL, 0, sizeof(unsigned long long), ctx->stream));
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_tile_max");
     k_tile_max<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, N, counters);
     SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
@@ -169,10 +170,12 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     SSG_TRY(reserveTables(ctx, len, tb, &numbered, &excl, &rank, &flags));
     const int64_t topRows = topBDev ? (overlap < ysize ? overlap : ysize) : 0;
     const int64_t leftCols = leftBDev ? (overlap < xsize ? overlap : xsize) : 0;
+    SSG_PROF_BEGIN(ctx, "k_tile_extents");
     k_tile_extents<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, ysize, xsize, topRows, leftCols, top, bottom,
                                                             left, right, tb);
     SSG_LAUNCHED(ctx);
     // mid = int(n / 2) of the strip's stitch axis (tiling.py:1297,1300)
+    SSG_PROF_BEGIN(ctx, "k_tile_flags");
     k_tile_flags<<<gridFor(len, 256), 256, 0, ctx->stream>>>(tb, len, topBDev != nullptr, leftBDev != nullptr,
                                                             (unsigned)(topRows / 2), (unsigned)(leftCols / 2), top,
                                                             bottom, left, right, flags, numbered);
@@ -180,8 +183,10 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, numbered, excl, (int)len, ctx->stream));
     SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, numbered, excl, (int)len, ctx->stream));
-    ctx->launches++;
+    SSG_LAUNCHED(ctx);
+    SSG_PROF_BEGIN(ctx, "k_tile_ranks");
     k_tile_ranks<<<gridFor(len, 256), 256, 0, ctx->stream>>>(numbered, excl, len, rank, counters);
     SSG_LAUNCHED(ctx);
 
@@ -192,11 +197,13 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
         SSG_TRY(ssg_reserve(ctx, ctx->stitch2, (size_t)(nTop + nLeft) * sizeof(unsigned long long)));
         unsigned long long *keys = bufp<unsigned long long>(ctx->stitch2);
         if (nTop > 0) {
+            SSG_PROF_BEGIN(ctx, "k_collect_pairs");
             k_collect_pairs<<<gridFor(nTop, 256), 256, 0, ctx->stream>>>(tileDev, xsize, topRows, xsize, topBDev, topBStride,
                                                                       flags, SSG_SEG_KEYTOP, 0ull, keys, counters);
             SSG_LAUNCHED(ctx);
         }
         if (nLeft > 0) {
+            SSG_PROF_BEGIN(ctx, "k_collect_pairs");
             k_collect_pairs<<<gridFor(nLeft, 256), 256, 0, ctx->stream>>>(tileDev, xsize, ysize, leftCols, leftBDev, leftBStride,
                                                                        flags, SSG_SEG_KEYLEFT, SSG_PAIR_LEFT, keys, counters);
             SSG_LAUNCHED(ctx);
@@ -212,13 +219,15 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
             unsigned *cnts = bufp<unsigned>(ctx->stitch5);
             SSG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keys, sorted, (int)M, 0, 64, ctx->stream));
             SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+            SSG_PROF_BEGIN(ctx, "cub_DeviceRadixSort_SortKeys");
             SSG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(ctx->cubTemp.p, tmpBytes, keys, sorted, (int)M, 0, 64, ctx->stream));
-            ctx->launches++;
+            SSG_LAUNCHED(ctx);
             unsigned long long *dRuns = counters + C_SCRATCH3;
             SSG_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(nullptr, tmpBytes, sorted, uniq, cnts, dRuns, (int)M, ctx->stream));
             SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+            SSG_PROF_BEGIN(ctx, "cub_DeviceRunLengthEncode_Encode");
             SSG_CUDA(ctx, cub::DeviceRunLengthEncode::Encode(ctx->cubTemp.p, tmpBytes, sorted, uniq, cnts, dRuns, (int)M, ctx->stream));
-            ctx->launches++;
+            SSG_LAUNCHED(ctx);
             SSG_TRY(ssg_fetch_counters(ctx));
             numPairs = (uint32_t)(ctx->hostCounters[C_SCRATCH3] & 0xffffffffu);
         }
@@ -290,6 +299,7 @@ extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64
     SSG_CUDA(ctx, cudaMemcpyAsync(ctx->lut.p, ctx->lutStage.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t wRows = bottom - top, wCols = right - left;
     if (wRows * wCols > 0) {
+        SSG_PROF_BEGIN(ctx, "k_apply_lut_window");
         k_apply_lut_window<<<gridFor(wRows * wCols, 256), 256, 0, ctx->stream>>>(
             tileDev, xsize, bufp<unsigned>(ctx->lut), top, left, wRows, wCols, outDev, outStride,
             reinterpret_cast<unsigned long long *>(histDev), histLen);

@@ -1,0 +1,839 @@
+"""
+Drop-in for pyshepseg.tiling.doTiledShepherdSegmentation on B200 GPUs.
+
+The raster is cut into the same overlapping tiles as the reference (getTilesForFile,
+tiling.py:376-443), every tile is segmented on a GPU with the same cluster centres
+(shepseg.doShepherdSegmentation, called at tiling.py:1446/1586) and the tiles are stitched
+with the reference's rules (stitchTiles / recodeTile / recodeSharedSegments /
+relabelSegments / crossesMidline, tiling.py:950-1306).  Segment labels never leave the
+device between segmentation and stitching: per-segment tables and the overlap votes are
+computed by kernels (ssg_tile_tables_device), the few thousand numbers per tile that the
+reference's sequential id bookkeeping needs come to the host (resolveTile below), and the
+final ids are applied on the device straight into the trimmed output window
+(ssg_apply_lut_device).
+
+What is kept from the reference's surface: the function signature, TiledSegmentationResult,
+SegmentationConcurrencyConfig (CONC_NONE and CONC_THREADS; a worker is a CUDA context on one
+of `devices`), TileInfo / getTilesForFile, PyShepSegTilingError, the timer names.  What is
+not rebuilt: the Fargate / subprocess managers and the TCP data channel (cloud
+orchestration).
+"""
+import atexit
+import ctypes
+import queue
+import sys
+import threading
+
+import numpy
+
+from . import _lib
+from . import rasterfile
+from . import shepseg
+from . import timinghooks
+
+DFLT_TILESIZE = 4096
+DFLT_OVERLAPSIZE = 1024
+DFLT_TEMPFILES_DRIVER = 'KEA'
+DFLT_TEMPFILES_EXT = 'kea'
+
+# the reference reads the k-means subsample in blocks of this size (tiling.py:94, 288)
+TILESIZE = 1024
+
+CONC_NONE = "CONC_NONE"
+CONC_THREADS = "CONC_THREADS"
+CONC_FARGATE = "CONC_FARGATE"
+CONC_SUBPROC = "CONC_SUBPROC"
+
+HORIZONTAL = 0
+VERTICAL = 1
+
+
+class PyShepSegTilingError(Exception):
+    pass
+
+
+class TiledSegmentationResult(object):
+    """Result of tiled segmentation (tiling.py:112-151)."""
+    def __init__(self):
+        self.maxSegId = None
+        self.numTileRows = None
+        self.numTileCols = None
+        self.subsamplePcnt = None
+        self.maxSpectralDiff = None
+        self.kmeans = None
+        self.hasEmptySegments = None
+        self.outDs = None
+        self.timings = None
+
+
+class SegmentationConcurrencyConfig(object):
+    """
+    Concurrency configuration (tiling.py:590-634).  concurrencyType CONC_NONE runs the tiles
+    one after the other on one GPU; CONC_THREADS runs `numWorkers` segmentation workers, each
+    a CUDA context of its own, dealt round-robin over `devices` (extension; default: GPU 0).
+    """
+    def __init__(self, concurrencyType=CONC_NONE, numWorkers=0, maxConcurrentReads=20,
+            tileCompletionTimeout=60, barrierTimeout=300, fargateCfg=None, devices=None):
+        self.concurrencyType = concurrencyType
+        self.numWorkers = numWorkers
+        self.maxConcurrentReads = maxConcurrentReads
+        self.tileCompletionTimeout = tileCompletionTimeout
+        self.barrierTimeout = barrierTimeout
+        self.fargateCfg = fargateCfg
+        self.devices = [0] if devices is None else list(devices)
+        if concurrencyType == CONC_FARGATE and fargateCfg is None:
+            raise PyShepSegTilingError("fargateCfg is required with CONC_FARGATE")
+        if concurrencyType != CONC_FARGATE and fargateCfg is not None:
+            raise PyShepSegTilingError("fargateCfg is only used with CONC_FARGATE")
+
+
+class TileInfo(object):
+    """Pixel coordinates of the tiles within an image (tiling.py:317-373)."""
+    def __init__(self):
+        self.tiles = {}
+        self.ncols = None
+        self.nrows = None
+
+    def addTile(self, xpos, ypos, xsize, ysize, col, row):
+        self.tiles[(col, row)] = (xpos, ypos, xsize, ysize)
+
+    def getNumTiles(self):
+        return len(self.tiles)
+
+    def getTile(self, col, row):
+        return self.tiles[(col, row)]
+
+
+def _axisSpans(rasterSize, tileSize, overlapSize):
+    """(pos, size) of the tiles along one axis: step tileSize-overlapSize, and the last tile
+    grows to the edge as soon as a further whole tile would not fit (tiling.py:414-438)."""
+    spans = []
+    pos = 0
+    while True:
+        size = tileSize
+        last = (pos + 2 * size) > rasterSize
+        if last:
+            size = rasterSize - pos
+        if size > 0:
+            spans.append((pos, size))
+        if last:
+            return spans
+        pos += tileSize - overlapSize
+
+
+def getTilesForFile(ds, tileSize, overlapSize):
+    """
+    TileInfo for a raster (tiling.py:376-443).  `ds` is anything with the raster size:
+    a rasterfile.RasterSource, a GDAL dataset or an (xsize, ysize) tuple.
+    """
+    if isinstance(ds, tuple):
+        (xs, ys) = ds
+    elif hasattr(ds, 'RasterXSize'):
+        (xs, ys) = (ds.RasterXSize, ds.RasterYSize)
+    else:
+        (xs, ys) = (ds.xsize, ds.ysize)
+    tileInfo = TileInfo()
+    cols = _axisSpans(int(xs), int(tileSize), int(overlapSize))
+    rows = _axisSpans(int(ys), int(tileSize), int(overlapSize))
+    for (r, (ypos, ysize)) in enumerate(rows):
+        for (c, (xpos, xsize)) in enumerate(cols):
+            tileInfo.addTile(xpos, ypos, xsize, ysize, c, r)
+    tileInfo.ncols = len(cols)
+    tileInfo.nrows = len(rows)
+    return tileInfo
+
+
+def getImgNullValue(src, bandNumbers):
+    """The raster's null value; all bands must agree (tiling.py:229-256)."""
+    vals = [src.nodata[b - 1] for b in bandNumbers]
+    if any(v != vals[0] for v in vals):
+        raise PyShepSegTilingError("Different null values in some bands")
+    return vals[0]
+
+
+def readSubsampledImage(src, bandNumbers, subsampleProp):
+    """
+    The pixel subsample used for the whole-file k-means fit: every skip-th row and column
+    inside each 1024 x 1024 block, blocks restarting the stride (tiling.py:259-314).
+    """
+    skip = int(round(1. / subsampleProp))
+
+    def picks(n):
+        return numpy.concatenate([numpy.arange(p, min(p + TILESIZE, n), skip)
+            for p in range(0, n, TILESIZE)])
+    rows = picks(src.ysize)
+    cols = picks(src.xsize)
+    out = numpy.empty((len(bandNumbers), len(rows), len(cols)), dtype=src.dtype)
+    for (i, r) in enumerate(rows):
+        line = src.readWindow(bandNumbers, 0, int(r), src.xsize, 1)
+        out[:, i, :] = line[:, 0, :][:, cols]
+    return out
+
+
+def fitSpectralClustersWholeFile(src, bandNumbers, numClusters=60, subsamplePcnt=None,
+        imgNullVal=None, fixedKMeansInit=False):
+    """
+    Fit the spectral clusters on a subsample of the whole raster (tiling.py:154-226).
+    Returns (kmeansObj, subsamplePcnt, imgNullVal).
+    """
+    if subsamplePcnt is None:
+        prop = min(1, numpy.sqrt(1000000 / (src.xsize * src.ysize)))
+        subsamplePcnt = 100 * prop**2
+    else:
+        prop = numpy.sqrt(subsamplePcnt / 100.0)
+    if imgNullVal is None:
+        imgNullVal = getImgNullValue(src, bandNumbers)
+    img = readSubsampledImage(src, bandNumbers, prop)
+    km = shepseg.fitSpectralClusters(img, numClusters, 100, imgNullVal, fixedKMeansInit)
+    return (km, subsamplePcnt, imgNullVal)
+
+
+# ---------------------------------------------------------------------------------------
+# stitching: the sequential part (host) around the two device phases
+# ---------------------------------------------------------------------------------------
+def tileMargins(tileInfo, col, row, xsize, ysize, overlapSize):
+    """Trimmed window [top,bottom) x [left,right) of a tile (tiling.py:997-1022)."""
+    margin = int(overlapSize / 2)
+    top = 0 if row == 0 else margin
+    left = 0 if col == 0 else margin
+    bottom = ysize if row == tileInfo.nrows - 1 else ysize - margin
+    right = xsize if col == tileInfo.ncols - 1 else xsize - margin
+    return (top, bottom, left, right)
+
+
+def _modeByKey(keys, values, counts):
+    """
+    For every distinct key: the value with the largest summed count, smallest value on ties
+    (scipy.stats.mode over the expanded list, tiling.py:1194).  Returns (keys, modes).
+    """
+    order = numpy.lexsort((values, keys))
+    (k, v, c) = (keys[order], values[order], counts[order].astype(numpy.int64))
+    newGroup = numpy.ones(len(k), dtype=bool)
+    newGroup[1:] = (k[1:] != k[:-1]) | (v[1:] != v[:-1])
+    starts = numpy.flatnonzero(newGroup)
+    (gk, gv, gc) = (k[starts], v[starts], numpy.add.reduceat(c, starts))
+    # inside one key the groups are in ascending value order; the first maximal count wins
+    best = numpy.lexsort((gv, -gc, gk))
+    firstOfKey = numpy.ones(len(best), dtype=bool)
+    firstOfKey[1:] = gk[best][1:] != gk[best][:-1]
+    sel = best[firstOfKey]
+    return (gk[sel], gv[sel])
+
+
+def resolveTile(tables, rank, flags, pairKeys, pairCounts, offset, lutTop, lutLeft,
+        simpleTileRecode=False):
+    """
+    The sequential step of the stitch for one tile (tiling.py:1024-1030, 1104-1126,
+    1247-1267): given the tile's local tables, the running id offset (maxSegId so far) and
+    the final-id tables of the upper / left neighbours, return (lut, trimmedMax).
+    """
+    n = int(tables.maxId) + 1
+    lut = numpy.zeros(n, dtype=numpy.uint32)
+    if simpleTileRecode:
+        lut[1:] = numpy.arange(1, n, dtype=numpy.uint64) + offset
+    else:
+        numbered = (flags & _lib.SEG_NUMBERED) != 0
+        lut[numbered] = rank[numbered] + numpy.uint32(offset)
+        if len(pairKeys) > 0:
+            isLeft = (pairKeys >> numpy.uint64(63)) != 0
+            segs = ((pairKeys >> numpy.uint64(32)) & numpy.uint64(0x7FFFFFFF)).astype(numpy.int64)
+            nbr = (pairKeys & numpy.uint64(0xFFFFFFFF)).astype(numpy.int64)
+            # top first, then left: the left vote overrides (tiling.py:1107-1121)
+            for (sel, nbrLut) in ((~isLeft, lutTop), (isLeft, lutLeft)):
+                if nbrLut is None or not sel.any():
+                    continue
+                (k, mode) = _modeByKey(segs[sel], nbrLut[nbr[sel]].astype(numpy.int64), pairCounts[sel])
+                lut[k] = mode.astype(numpy.uint32)
+    inTrim = (flags & _lib.SEG_INTRIM) != 0
+    trimmedMax = int(lut[inTrim].max()) if inTrim.any() else 0
+    return (lut, trimmedMax)
+
+
+class _DevicePool(object):
+    """Reuses device buffers: cudaMalloc / cudaFree synchronise the whole device.  Shared by
+    the worker threads of one device; every call goes through the caller's own context."""
+    def __init__(self):
+        self.free = []
+        self.lock = threading.Lock()
+
+    def get(self, ctx, nbytes):
+        with self.lock:
+            best = None
+            for (i, (cap, p)) in enumerate(self.free):
+                if cap >= nbytes and (best is None or cap < self.free[best][0]):
+                    best = i
+            if best is not None:
+                return self.free.pop(best)
+        return (nbytes, ctx.dev_alloc(nbytes))
+
+    def put(self, buf):
+        with self.lock:
+            self.free.append(buf)
+
+    def close(self, ctx):
+        with self.lock:
+            for (cap, p) in self.free:
+                ctx.dev_free(p)
+            self.free = []
+
+
+class _Slot(object):
+    """A context with its staging memory, kept alive between calls: creating contexts and
+    pinned / device buffers costs far more than segmenting a tile."""
+    def __init__(self, device):
+        self.ctx = _lib.Context(device)
+        self.pinned = None       # PinnedArray staging of one tile image
+        self.devStage = None     # (cap, ptr): tile image gathered from a DeviceRaster
+        self.window = None       # PinnedArray staging of one trimmed output window
+        self.winDev = None       # (cap, ptr)
+        self.lock = threading.Lock()
+
+    def pinnedFor(self, nItems, dtype):
+        nbytes = nItems * numpy.dtype(dtype).itemsize
+        if self.pinned is None or self.pinned.array.nbytes < nbytes:
+            if self.pinned is not None:
+                self.pinned.free()
+            self.pinned = _lib.PinnedArray((nbytes,), numpy.uint8)
+        return self.pinned.array[:nbytes].view(dtype)
+
+    def devStageFor(self, nbytes):
+        if self.devStage is None or self.devStage[0] < nbytes:
+            if self.devStage is not None:
+                self.ctx.dev_free(self.devStage[1])
+            self.devStage = (nbytes, self.ctx.dev_alloc(nbytes))
+        return self.devStage[1]
+
+    def windowFor(self, nItems):
+        if self.window is None or self.window.array.size < nItems:
+            if self.window is not None:
+                self.window.free()
+            self.window = _lib.PinnedArray((nItems,), numpy.uint32)
+        if self.winDev is None or self.winDev[0] < nItems * 4:
+            if self.winDev is not None:
+                self.ctx.dev_free(self.winDev[1])
+            self.winDev = (nItems * 4, self.ctx.dev_alloc(nItems * 4))
+        return (self.window.array, self.winDev[1])
+
+    def close(self):
+        if self.pinned is not None:
+            self.pinned.free()
+        if self.window is not None:
+            self.window.free()
+        if self.devStage is not None:
+            self.ctx.dev_free(self.devStage[1])
+        if self.winDev is not None:
+            self.ctx.dev_free(self.winDev[1])
+        self.ctx.close()
+
+
+class _GpuState(object):
+    """Everything kept per device between calls: slot 0 is the stitch / sequential context,
+    slots 1.. are the segmentation workers; one pool of per-tile label buffers."""
+    def __init__(self, device):
+        self.device = device
+        self.slots = []
+        self.pool = _DevicePool()
+        self.lock = threading.Lock()
+
+    def slot(self, i):
+        with self.lock:
+            while len(self.slots) <= i:
+                self.slots.append(_Slot(self.device))
+            return self.slots[i]
+
+    def close(self):
+        if self.slots:
+            self.pool.close(self.slots[0].ctx)
+        for sl in self.slots:
+            sl.close()
+        self.slots = []
+
+
+_gpuStates = {}
+_gpuStatesLock = threading.Lock()
+
+
+def gpuState(device):
+    with _gpuStatesLock:
+        if device not in _gpuStates:
+            _gpuStates[device] = _GpuState(device)
+        return _gpuStates[device]
+
+
+def releaseGpuState():
+    """Free the contexts, pinned staging and device buffers kept between calls."""
+    with _gpuStatesLock:
+        for st in _gpuStates.values():
+            st.close()
+        _gpuStates.clear()
+
+
+atexit.register(releaseGpuState)
+
+
+class _Tile(object):
+    def __init__(self, col, row, geom):
+        (self.col, self.row) = (col, row)
+        (self.xpos, self.ypos, self.xsize, self.ysize) = geom
+        self.buf = None          # (capacity, device pointer) of the local labels
+        self.numSegments = 0
+        self.lut = None          # final id of every local id, once resolved
+        self.uses = 0            # neighbours that still need the local labels
+        self.done = threading.Event()
+        self.error = None
+        self.result = None
+
+
+class TiledSegmenter(object):
+    """
+    Segments the tiles of one raster and stitches them.  One instance per call of
+    doTiledShepherdSegmentation; bench.py drives it directly with the raster in pinned host
+    memory or in HBM.
+    """
+    def __init__(self, src, bandNumbers, tileInfo, overlapSize, centres, imgNullVal, fourConnected,
+            minSegmentSize, thr, simpleTileRecode, concurrencyCfg, timings, verbose=False,
+            profile=False):
+        self.src = src
+        self.bandNumbers = list(bandNumbers)
+        self.tileInfo = tileInfo
+        self.overlapSize = int(overlapSize)
+        self.centres = centres
+        self.imgNullVal = imgNullVal
+        self.fourConnected = fourConnected
+        self.minSegmentSize = minSegmentSize
+        self.thr = thr
+        self.simple = simpleTileRecode
+        self.cfg = concurrencyCfg
+        self.timings = timings
+        self.verbose = verbose
+        self.profile = profile
+        self.order = sorted(tileInfo.tiles.keys(), key=lambda cr: (cr[1], cr[0]))
+        self.tiles = dict((cr, _Tile(cr[0], cr[1], tileInfo.tiles[cr])) for cr in self.order)
+        for t in self.tiles.values():
+            t.uses = int(t.col + 1 < tileInfo.ncols) + int(t.row + 1 < tileInfo.nrows)
+            if (t.ysize < self.overlapSize or t.xsize < self.overlapSize) and len(self.tiles) > 1:
+                raise PyShepSegTilingError("tiles must be at least overlapSize pixels on a side")
+        if len(set(self.cfg.devices)) > 1:
+            raise PyShepSegTilingError('one process drives one GPU; use one process per GPU '
+                '(torchrun) for more, as bench.py --gpus N does')
+        self.device = self.cfg.devices[0]
+        self.readSemaphore = threading.BoundedSemaphore(max(1, self.cfg.maxConcurrentReads))
+        self.forceExit = threading.Event()
+        self.stageMs = {'assign': 0.0, 'clump': 0.0, 'single': 0.0, 'small': 0.0, 'total': 0.0}
+        self.launches = 0
+        self.h2dBytes = 0
+        self.d2hBytes = 0
+        self.kernelMs = {}       # name -> [count, total ms] when profile=True
+        self.statLock = threading.Lock()
+
+    # ---- segmentation of one tile on a slot --------------------------------------------------
+    def segmentOne(self, slot, pool, tile):
+        ctx = slot.ctx
+        dtype = self.src.dtype.newbyteorder('=')
+        item = dtype.itemsize
+        nB = len(self.bandNumbers)
+        nPix = tile.ysize * tile.xsize
+        direct = self._directSource()
+        with self.timings.interval('reading'):
+            if direct is not None:
+                # the raster is addressable memory (HBM, or host memory that cudaMemcpy2D can
+                # read in place): gather the tile's window band by band, no host staging copy
+                (base, onDevice) = direct
+                imgDev = slot.devStageFor(nB * nPix * item)
+                copy = 'ssg_memcpy2d_d2d' if onDevice else 'ssg_memcpy2d_h2d'
+                for (i, b) in enumerate(self.bandNumbers):
+                    srcPtr = base + ((b - 1) * self.src.ysize * self.src.xsize +
+                        tile.ypos * self.src.xsize + tile.xpos) * item
+                    ctx.call(copy, imgDev + i * nPix * item, tile.xsize * item, srcPtr,
+                        self.src.xsize * item, tile.xsize * item, tile.ysize)
+            else:
+                with self.readSemaphore:
+                    img = slot.pinnedFor(nB * nPix, dtype).reshape(nB, tile.ysize, tile.xsize)
+                    self.src.readWindow(self.bandNumbers, tile.xpos, tile.ypos, tile.xsize, tile.ysize,
+                        out=img)
+        with self.timings.interval('segmentation'):
+            if direct is None:
+                ctx.call('ssg_upload_image', _lib.ptr(img), _lib.DTYPE_CODES[numpy.dtype(dtype)], nB,
+                    tile.ysize, tile.xsize)
+                imgDev = ctx.lib.ssg_staged_image(ctx.h)
+            tile.buf = pool.get(ctx, nPix * 4)
+            prm = shepseg.makeTileParams(dtype, nB, tile.ysize, tile.xsize, self.centres,
+                self.imgNullVal, self.fourConnected, self.minSegmentSize, self.thr)
+            res = _lib.TileResult()
+            ctx.call('ssg_segment_tile_device', imgDev, ctypes.byref(prm), tile.buf[1], ctypes.byref(res))
+        tile.numSegments = int(res.numSegments)
+        tile.result = res
+        with self.statLock:
+            if not isinstance(self.src, DeviceRaster):
+                self.h2dBytes += nB * nPix * item
+            for k in self.stageMs:
+                self.stageMs[k] += getattr(res, 'ms' + k.capitalize())
+
+    def _directSource(self):
+        """(base pointer, on device?) when tile windows can be copied straight out of the
+        raster's memory, else None (file sources go through a pinned staging read)."""
+        if isinstance(self.src, DeviceRaster):
+            return (self.src.devPtr, True)
+        if isinstance(self.src, rasterfile.MemoryRaster) and not isinstance(self.src, rasterfile.NpySource):
+            a = self.src.img
+            if isinstance(a, numpy.ndarray) and a.flags.c_contiguous and a.dtype.isnative and \
+                    a.dtype in _lib.DTYPE_CODES:
+                return (a.ctypes.data, False)
+        return None
+
+    def _worker(self, slot, pool, inQue):
+        """A segmentation worker (tiling.py:1560-1613): pops tiles until the queue is empty."""
+        with slot.lock:
+            before = slot.ctx.launch_count()
+            self._profileStart(slot)
+            while not self.forceExit.is_set():
+                try:
+                    cr = inQue.get(block=False)
+                except queue.Empty:
+                    break
+                tile = self.tiles[cr]
+                try:
+                    self.segmentOne(slot, pool, tile)
+                except Exception as e:     # reported by the stitch loop, like WorkerErrorRecord
+                    tile.error = e
+                    self.forceExit.set()
+                tile.done.set()
+            self._profileStop(slot)
+            with self.statLock:
+                self.launches += slot.ctx.launch_count() - before
+
+    def _profileStart(self, slot):
+        if self.profile:
+            slot.ctx.call('ssg_profile_enable', 1)
+
+    def _profileStop(self, slot):
+        if not self.profile:
+            return
+        buf = ctypes.create_string_buffer(1 << 16)
+        slot.ctx.call('ssg_profile_fetch', buf, len(buf))
+        slot.ctx.call('ssg_profile_enable', 0)
+        with self.statLock:
+            for line in buf.value.decode().splitlines():
+                (name, cnt, ms) = line.split()
+                ent = self.kernelMs.setdefault(name, [0, 0.0])
+                ent[0] += int(cnt)
+                ent[1] += float(ms)
+
+    # ---- the stitch of one tile (main thread) ------------------------------------------------
+    def stitchOne(self, slot, pool, tile, offset, sink, hist):
+        ctx = slot.ctx
+        ti = self.tileInfo
+        (top, bottom, left, right) = tileMargins(ti, tile.col, tile.row, tile.xsize, tile.ysize,
+            self.overlapSize)
+        ov = self.overlapSize
+        up = self.tiles.get((tile.col, tile.row - 1)) if tile.row > 0 else None
+        lf = self.tiles.get((tile.col - 1, tile.row)) if tile.col > 0 else None
+        topB = leftB = None
+        (topStride, leftStride) = (0, 0)
+        if not self.simple:
+            if up is not None:      # the upper tile's bottom `ov` rows (its LOCAL labels)
+                topB = up.buf[1] + (up.ysize - ov) * up.xsize * 4
+                topStride = up.xsize
+            if lf is not None:      # the left tile's right `ov` columns
+                leftB = lf.buf[1] + (lf.xsize - ov) * 4
+                leftStride = lf.xsize
+        tables = _lib.TileTables()
+        ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, ov, topB, topStride,
+            leftB, leftStride, top, bottom, left, right, ctypes.byref(tables))
+        n = int(tables.maxId) + 1
+        rank = numpy.empty(n, dtype=numpy.uint32)
+        flags = numpy.empty(n, dtype=numpy.uint8)
+        pairKeys = numpy.empty(int(tables.numPairs), dtype=numpy.uint64)
+        pairCounts = numpy.empty(int(tables.numPairs), dtype=numpy.uint32)
+        ctx.call('ssg_tile_tables_fetch', _lib.ptr(rank), _lib.ptr(flags), _lib.ptr(pairKeys),
+            _lib.ptr(pairCounts))
+        (lut, trimmedMax) = resolveTile(tables, rank, flags, pairKeys, pairCounts, offset,
+            None if up is None else up.lut, None if lf is None else lf.lut, self.simple)
+        tile.lut = lut
+        # final ids over the trimmed window, on the device, then to the output raster
+        (wr, wc) = (bottom - top, right - left)
+        hist.ensure(ctx, max(offset + int(tables.countNew), trimmedMax, int(lut.max()) if n else 0) + 1)
+        xout = tile.xpos + left
+        yout = tile.ypos + top
+        if isinstance(sink, DeviceMosaicSink):
+            # the mosaic lives in HBM: write the window in place
+            ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
+                int(tables.maxId), top, bottom, left, right,
+                sink.devPtr + (yout * sink.xsize + xout) * 4, sink.xsize, hist.dev, hist.cap)
+        else:
+            (window, winDev) = slot.windowFor(wr * wc)
+            ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
+                int(tables.maxId), top, bottom, left, right, winDev, wc, hist.dev, hist.cap)
+            arr = getattr(sink, 'array', None)
+            if (type(sink) is rasterfile.MemorySink and isinstance(arr, numpy.ndarray) and
+                    arr.flags.c_contiguous and arr.dtype == numpy.uint32):
+                # the output raster is plain host memory: land the window in place
+                ctx.call('ssg_memcpy2d_d2h', arr.ctypes.data + (yout * arr.shape[1] + xout) * 4,
+                    arr.shape[1] * 4, winDev, wc * 4, wc * 4, wr)
+            else:
+                out = window[:wr * wc].reshape(wr, wc)
+                ctx.call('ssg_memcpy_d2h', _lib.ptr(out), winDev, wr * wc * 4)
+                sink.write(out, xout, yout)
+                sink.writeOverviews(out, xout, yout)
+            self.d2hBytes += wr * wc * 4
+        self.d2hBytes += rank.nbytes + flags.nbytes + pairKeys.nbytes + pairCounts.nbytes
+        self.h2dBytes += lut.nbytes
+        # the neighbours' labels are no longer needed once both users have run
+        for nb in (up, lf):
+            if nb is not None:
+                nb.uses -= 1
+                if nb.uses == 0 and nb.buf is not None:
+                    pool.put(nb.buf)
+                    nb.buf = None
+        if tile.uses == 0:
+            pool.put(tile.buf)
+            tile.buf = None
+        return max(offset, trimmedMax)
+
+    # ---- driver ----------------------------------------------------------------------------
+    def run(self, sink):
+        """Segment and stitch every tile; returns (maxSegId, histogram)."""
+        cfg = self.cfg
+        state = gpuState(self.device)
+        pool = state.pool
+        main = state.slot(0)
+        hist = _DeviceHistogram()
+        offset = 0
+        workers = []
+        numWorkers = cfg.numWorkers if cfg.concurrencyType == CONC_THREADS else 0
+        main.lock.acquire()
+        before = main.ctx.launch_count()
+        try:
+            self._profileStart(main)
+            if numWorkers > 0:
+                inQue = queue.Queue()
+                for cr in self.order:
+                    inQue.put(cr)
+                with self.timings.interval('startworkers'):
+                    for w in range(numWorkers):
+                        th = threading.Thread(target=self._worker, args=(state.slot(1 + w), pool, inQue),
+                            daemon=True)
+                        th.start()
+                        workers.append(th)
+            with self.timings.interval('stitchtiles') if numWorkers > 0 else _nullContext():
+                for cr in self.order:
+                    tile = self.tiles[cr]
+                    if numWorkers > 0:
+                        if not tile.done.wait(cfg.tileCompletionTimeout):
+                            self.forceExit.set()
+                            raise PyShepSegTilingError(("Timeout ({} seconds) waiting for completed "
+                                "tile. Try increasing tileCompletionTimeout").format(cfg.tileCompletionTimeout))
+                        if tile.error is not None:
+                            raise PyShepSegTilingError("A segmentation worker failed on tile "
+                                "col={} row={}: {}".format(tile.col, tile.row, tile.error))
+                        offset = self.stitchOne(main, pool, tile, offset, sink, hist)
+                    else:
+                        if self.verbose:
+                            print("Doing tile row={}, col={}".format(tile.row, tile.col))
+                        self.segmentOne(main, pool, tile)
+                        with self.timings.interval('stitchtiles'):
+                            offset = self.stitchOne(main, pool, tile, offset, sink, hist)
+            histogram = hist.fetch(main.ctx, offset + 1)
+            self.d2hBytes += histogram.nbytes
+        finally:
+            self.forceExit.set()
+            for th in workers:
+                th.join()
+            try:
+                self._profileStop(main)
+                hist.close(main.ctx)
+                for t in self.tiles.values():
+                    if t.buf is not None:
+                        pool.put(t.buf)
+                        t.buf = None
+                self.launches += main.ctx.launch_count() - before
+            finally:
+                main.lock.release()
+        return (offset, histogram)
+
+
+class DeviceRaster(rasterfile.RasterSource):
+    """A band-sequential (count, ysize, xsize) raster that already lives in GPU memory
+    (devPtr is a device pointer on the segmenting GPU).  Used to measure the path with its
+    input resident in HBM; tiles are gathered with device-to-device copies."""
+    def __init__(self, devPtr, count, ysize, xsize, dtype, nodata=None):
+        self.devPtr = int(devPtr)
+        (self.count, self.ysize, self.xsize) = (int(count), int(ysize), int(xsize))
+        self.dtype = numpy.dtype(dtype)
+        self.nodata = [nodata] * self.count
+
+
+class DeviceMosaicSink(rasterfile.RasterSink):
+    """A uint32 (ysize, xsize) output mosaic in GPU memory: the stitch writes the trimmed
+    windows in place and nothing but the small per-tile tables crosses PCIe."""
+    def __init__(self, devPtr, xsize, ysize):
+        self.devPtr = int(devPtr)
+        (self.xsize, self.ysize) = (int(xsize), int(ysize))
+        self.metadata = {}
+        self.hist = None
+
+    def setMetadataItem(self, key, value):
+        self.metadata[key] = value
+
+    def writeHistogram(self, hist):
+        self.hist = hist
+
+
+class _nullContext(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class _DeviceHistogram(object):
+    """Growing uint64 histogram on the device (HistogramAccumulator, tiling.py:1915-1963)."""
+    def __init__(self):
+        self.dev = None
+        self.cap = 0
+
+    def ensure(self, ctx, n):
+        if n <= self.cap:
+            return
+        newCap = max(n, 2 * self.cap, 1 << 16)
+        p = ctx.dev_alloc(newCap * 8)
+        ctx.call('ssg_memset_d', p, 0, newCap * 8)
+        if self.dev is not None:
+            ctx.call('ssg_memcpy_d2d', p, self.dev, self.cap * 8)
+            ctx.synchronize()
+            ctx.dev_free(self.dev)
+        (self.dev, self.cap) = (p, newCap)
+
+    def fetch(self, ctx, n):
+        h = numpy.zeros(n, dtype=numpy.uint64)
+        if self.dev is not None and n > 0:
+            m = min(n, self.cap)
+            ctx.call('ssg_memcpy_d2h', _lib.ptr(h), self.dev, m * 8)
+        if n > 0:
+            h[0] = 0     # the null count is always removed (tiling.py:1930-1931)
+        return h.astype(numpy.float64)
+
+    def close(self, ctx):
+        if self.dev is not None:
+            ctx.dev_free(self.dev)
+            self.dev = None
+
+
+def estimateStatsFromHisto(sink, hist):
+    """STATISTICS_* metadata from the histogram (utils.estimateStatsFromHisto, utils.py:47-95)."""
+    if hist.sum() <= 0:
+        return
+    present = numpy.flatnonzero(hist > 0)
+    values = numpy.arange(len(hist))
+    nVals = hist.sum()
+    meanVal = (values * hist).sum() / nVals
+    stdDevVal = numpy.sqrt((hist * numpy.power(values - meanVal, 2)).sum() / nVals)
+    medianVal = numpy.flatnonzero(hist.cumsum() >= nVals / 2)[0]
+    sink.setMetadataItem("STATISTICS_MINIMUM", repr(int(present[0])))
+    sink.setMetadataItem("STATISTICS_MAXIMUM", repr(int(present[-1])))
+    sink.setMetadataItem("STATISTICS_MEAN", repr(float(meanVal)))
+    sink.setMetadataItem("STATISTICS_STDDEV", repr(float(stdDevVal)))
+    sink.setMetadataItem("STATISTICS_MODE", repr(int(numpy.argmax(hist))))
+    sink.setMetadataItem("STATISTICS_MEDIAN", repr(int(medianVal)))
+    sink.setMetadataItem("STATISTICS_SKIPFACTORX", "1")
+    sink.setMetadataItem("STATISTICS_SKIPFACTORY", "1")
+    sink.setMetadataItem("STATISTICS_HISTOBINFUNCTION", "direct")
+
+
+def checkForEmptySegments(hist, overlapSize):
+    """Warn about segment ids with no pixels (tiling.py:1308-1341).  Unlike the reference,
+    whose function forgets to return it, the flag is returned."""
+    empty = numpy.where(hist[1:] == 0)[0] + 1
+    if len(empty) > 0:
+        print("\nWARNING: Found {} segments with zero pixels\n    Segment IDs: {}\n"
+            "    This is caused by inconsistent joining of segmentation\n"
+            "    tiles, and will probably cause trouble later on.\n"
+            "    It is highly recommended to re-run with a larger overlap\n"
+            "    size (currently {}), and if necessary a larger tile size\n".format(
+                len(empty), empty, overlapSize), file=sys.stderr)
+    return len(empty) > 0
+
+
+def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
+        overlapSize=DFLT_OVERLAPSIZE, minSegmentSize=50, numClusters=60,
+        bandNumbers=None, subsamplePcnt=None, maxSpectralDiff='auto',
+        imgNullVal=None, fixedKMeansInit=False, fourConnected=True,
+        verbose=False, simpleTileRecode=False, outputDriver='KEA',
+        creationOptions=[], spectDistPcntile=50, kmeansObj=None,
+        tempfilesDriver=DFLT_TEMPFILES_DRIVER, tempfilesExt=DFLT_TEMPFILES_EXT,
+        tempfilesCreationOptions=[], writeHistogram=True, returnGDALDS=False,
+        concurrencyCfg=None):
+    """
+    Run the Shepherd segmentation on a raster file tile by tile and stitch the tiles into
+    one output raster (tiling.py:446-571).  Parameters as in the reference.  The temp-file
+    arguments are accepted and ignored: tiles never go to disk, they stay in GPU memory until
+    they are stitched.  outputDriver must be one GDAL offers, or 'GTiff' / 'NPY' / 'MEM' of the
+    built-in writer when GDAL is absent.  With returnGDALDS the result's outDs is the open
+    output object (a GDAL dataset with GDAL, else the rasterfile sink).
+    """
+    if concurrencyCfg is None:
+        concurrencyCfg = SegmentationConcurrencyConfig()
+    if concurrencyCfg.concurrencyType not in (CONC_NONE, CONC_THREADS):
+        if concurrencyCfg.concurrencyType in (CONC_FARGATE, CONC_SUBPROC):
+            raise PyShepSegTilingError("concurrencyType {} is not part of the B200 build; use "
+                "CONC_NONE or CONC_THREADS".format(concurrencyCfg.concurrencyType))
+        raise ValueError("Unknown concurrencyType '{}'".format(concurrencyCfg.concurrencyType))
+    if (overlapSize % 2) != 0:
+        raise PyShepSegTilingError("Overlap size must be an even number")
+    if not isinstance(outfile, rasterfile.RasterSink) and not rasterfile.driverAvailable(outputDriver):
+        raise PyShepSegTilingError("This build does not support driver '{}'".format(outputDriver))
+
+    timings = timinghooks.Timers()
+    result = TiledSegmentationResult()
+    with timings.interval('walltime'):
+        try:
+            src = rasterfile.openRaster(infile)
+        except rasterfile.RasterError as e:
+            raise PyShepSegTilingError(str(e))
+        if bandNumbers is None:
+            bandNumbers = range(1, src.count + 1)
+        if kmeansObj is None:
+            with timings.interval('spectralclusters'):
+                (kmeansObj, subsamplePcnt, imgNullVal) = fitSpectralClustersWholeFile(src,
+                    bandNumbers, numClusters, subsamplePcnt, imgNullVal, fixedKMeansInit)
+        elif imgNullVal is None:
+            imgNullVal = getImgNullValue(src, bandNumbers)
+        tileInfo = getTilesForFile(src, tileSize, overlapSize)
+        if verbose:
+            print("Found {} tiles, with {} rows and {} cols".format(tileInfo.getNumTiles(),
+                tileInfo.nrows, tileInfo.ncols))
+        msd = shepseg.autoMaxSpectralDiff(kmeansObj, maxSpectralDiff, spectDistPcntile)
+        try:
+            sink = rasterfile.createRaster(outfile, src.xsize, src.ysize, outputDriver,
+                creationOptions, source=src)
+        except rasterfile.RasterError as e:
+            raise PyShepSegTilingError(str(e))
+        sink.setMetadataItem('LAYER_TYPE', 'thematic')
+        sink.setNoData(shepseg.SEGNULLVAL)
+        seg = TiledSegmenter(src, bandNumbers, tileInfo, overlapSize, shepseg._centres(kmeansObj),
+            imgNullVal, fourConnected, minSegmentSize, shepseg.spectralThreshold(msd),
+            simpleTileRecode, concurrencyCfg, timings, verbose)
+        (maxSegId, hist) = seg.run(sink)
+        sink.writeHistogram(hist)
+        result.hasEmptySegments = checkForEmptySegments(hist, overlapSize)
+        estimateStatsFromHisto(sink, hist)
+        if returnGDALDS:
+            result.outDs = getattr(sink, 'ds', sink)
+        else:
+            sink.close()
+        if not isinstance(infile, rasterfile.RasterSource):
+            src.close()
+
+    result.maxSegId = maxSegId
+    result.numTileRows = tileInfo.nrows
+    result.numTileCols = tileInfo.ncols
+    result.subsamplePcnt = subsamplePcnt
+    result.maxSpectralDiff = msd
+    result.kmeans = kmeansObj
+    result.timings = timings
+    result.stageMs = seg.stageMs
+    result.gpuLaunches = seg.launches
+    result.h2dBytes = seg.h2dBytes
+    result.d2hBytes = seg.d2hBytes
+    return result

@@ -1,0 +1,138 @@
+"""
+GPU parity tests of the tiled path: pyshepseg_b200.tiling.doTiledShepherdSegmentation against
+the mosaics the unmodified reference wrote (tests/golden/tiled_*.npz) and against the CPU
+oracle's per-tile segmentation + stitch on larger seeded rasters.  Bit-exact label rasters,
+histograms and maxSegId.
+"""
+import numpy
+import pytest
+
+import goldenutil
+from oracle import oracle
+from pyshepseg_b200 import synth, rasterfile
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def tiling():
+    from pyshepseg_b200 import tiling as mod
+    return mod
+
+
+def same(got, want, what):
+    got = numpy.asarray(got)
+    want = numpy.asarray(want)
+    assert got.shape == want.shape, '%s: shape %s != %s' % (what, got.shape, want.shape)
+    if not numpy.array_equal(got, want):
+        bad = numpy.argwhere(got != want)
+        first = tuple(bad[0])
+        raise AssertionError('%s: %d of %d differ; first at %s: got %s want %s' % (
+            what, len(bad), got.size, first, got[first], want[first]))
+
+
+def run_tiled(tiling, img, km, m, cfg=None, nullVal='meta'):
+    src = rasterfile.MemoryRaster(img, nodata=m['imgNullVal'])
+    res = tiling.doTiledShepherdSegmentation(src, None, tileSize=m['tileSize'],
+        overlapSize=m['overlapSize'], minSegmentSize=m['minSegmentSize'],
+        numClusters=m['numClusters'], imgNullVal=m['imgNullVal'],
+        fourConnected=m['fourConnected'], kmeansObj=km,
+        simpleTileRecode=m['simpleTileRecode'], outputDriver='MEM', returnGDALDS=True,
+        concurrencyCfg=cfg)
+    return res
+
+
+@pytest.mark.parametrize('name', goldenutil.tiled_names())
+def test_golden_tiled(tiling, name):
+    c = goldenutil.load(name)
+    m = c['meta']
+    res = run_tiled(tiling, c['img'], goldenutil.Centres(c['centres']), m)
+    assert res.numTileRows == m['numTileRows'] and res.numTileCols == m['numTileCols']
+    same(res.outDs.array, c['mosaic'], 'mosaic')
+    assert int(res.maxSegId) == m['maxSegId']
+    same(res.outDs.hist, c['hist'], 'histogram')
+    assert float(res.maxSpectralDiff) == m['maxSpectralDiff']
+    assert res.outDs.nodata == 0
+    assert res.outDs.metadata['LAYER_TYPE'] == 'thematic'
+    for name in ('walltime', 'reading', 'segmentation', 'stitchtiles'):
+        assert res.timings.getDurationsForName(name) is not None
+
+
+@pytest.mark.parametrize('name', ['tiled_700x900', 'tiled_640_5x5_8conn'])
+def test_threads_equal_sequential(tiling, name):
+    c = goldenutil.load(name)
+    m = c['meta']
+    cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=3)
+    res = run_tiled(tiling, c['img'], goldenutil.Centres(c['centres']), m, cfg)
+    same(res.outDs.array, c['mosaic'], 'mosaic (3 workers)')
+    assert int(res.maxSegId) == m['maxSegId']
+    same(res.outDs.hist, c['hist'], 'histogram (3 workers)')
+    assert res.timings.getDurationsForName('startworkers') is not None
+
+
+def oracle_tiled(img, km, tileSize, overlap, minSeg, nullVal, four, simple=False):
+    (nB, nR, nC) = img.shape
+    ti = oracle.getTilesForFile(nC, nR, tileSize, overlap)
+    segs = {}
+    for ((col, row), (x, y, xs, ys)) in ti.tiles.items():
+        sub = numpy.ascontiguousarray(img[:, y:y + ys, x:x + xs])
+        segs[(col, row)] = oracle.doShepherdSegmentation(sub, minSegmentSize=minSeg, imgNullVal=nullVal,
+            fourConnected=four, kmeansObj=km).segimg
+    return oracle.stitchTiles(segs, ti, nC, nR, overlap, simpleTileRecode=simple)
+
+
+CASES = [
+    ('wide_2000x2600', (2000, 2600, 4), 512, 128, 40, 40, 0.0, True),
+    ('null_1500x1700_8conn', (1500, 1700, 3), 400, 100, 30, 30, 0.15, False),
+    ('small_overlap', (1300, 1200, 3), 300, 20, 20, 25, 0.0, True),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_tiled_against_oracle(tiling, case):
+    (name, (r, c, b), tileSize, overlap, k, minSeg, nullFrac, four) = case
+    img = synth.synth_v1(r, c, b, seed=len(name) + 40, nullFrac=nullFrac)
+    nullVal = 0 if nullFrac > 0 else None
+    km = goldenutil.Centres(synth.diagonal_centres(img, k, nullVal))
+    (mosaic, maxSegId, hist) = oracle_tiled(img, km, tileSize, overlap, minSeg, nullVal, four)
+    m = {'tileSize': tileSize, 'overlapSize': overlap, 'minSegmentSize': minSeg, 'numClusters': k,
+        'imgNullVal': nullVal, 'fourConnected': four, 'simpleTileRecode': False}
+    res = run_tiled(tiling, img, km, m)
+    same(res.outDs.array, mosaic, name + ' mosaic')
+    assert int(res.maxSegId) == maxSegId
+    same(res.outDs.hist, hist, name + ' histogram')
+    # the tiled partition equals the whole-image partition away from nothing: every label id
+    # 1..maxSegId that has pixels is connected-consistent with the oracle (checked by equality)
+
+
+def test_file_to_file(tiling, tmp_path):
+    """GeoTIFF in, GeoTIFF out, through the built-in reader / writer; null value from the file"""
+    img = synth.synth_v1(900, 1000, 4, seed=77, nullFrac=0.1)
+    km = goldenutil.Centres(synth.diagonal_centres(img, 20, 0))
+    infile = str(tmp_path / 'in.tif')
+    outfile = str(tmp_path / 'out.tif')
+    rasterfile.writeImage(infile, img, nodata=0)
+    res = tiling.doTiledShepherdSegmentation(infile, outfile, tileSize=400, overlapSize=100,
+        minSegmentSize=30, kmeansObj=km, outputDriver='GTiff')
+    (mosaic, maxSegId, hist) = oracle_tiled(img, km, 400, 100, 30, 0, True)
+    out = rasterfile.openRaster(outfile)
+    same(out.readWindow([1], 0, 0, 1000, 900)[0], mosaic, 'file mosaic')
+    assert out.nodata == [0]
+    assert int(res.maxSegId) == maxSegId
+    same(numpy.load(outfile + '.hist.npy'), hist, 'file histogram')
+    out.close()
+
+
+def test_whole_file_kmeans_fit(tiling):
+    """kmeansObj=None: the subsample fit runs on the host (scikit-learn) and the result carries
+    it; determinism of the segmentation given those centres is checked against the oracle"""
+    img = synth.synth_v1(800, 900, 3, seed=5)
+    src = rasterfile.MemoryRaster(img)
+    res = tiling.doTiledShepherdSegmentation(src, None, tileSize=512, overlapSize=64,
+        minSegmentSize=30, numClusters=12, fixedKMeansInit=True, outputDriver='MEM',
+        returnGDALDS=True)
+    assert res.kmeans.cluster_centers_.shape == (12, 3)
+    assert 0 < res.subsamplePcnt <= 100
+    (mosaic, maxSegId, hist) = oracle_tiled(img, res.kmeans, 512, 64, 30, None, True)
+    same(res.outDs.array, mosaic, 'mosaic with fitted centres')
+    assert res.timings.getDurationsForName('spectralclusters') is not None

@@ -1,0 +1,103 @@
+"""Host-side raster I/O used by the tiled driver (no GPU needed)."""
+import os
+
+import numpy
+import pytest
+
+from pyshepseg_b200 import rasterfile, tiling, timinghooks
+from oracle import oracle
+
+
+@pytest.mark.parametrize('dtype', [numpy.uint8, numpy.uint16, numpy.int16])
+def test_tiff_roundtrip_windows(tmp_path, dtype):
+    rng = numpy.random.default_rng(3)
+    info = numpy.iinfo(dtype)
+    img = rng.integers(info.min, info.max, (3, 57, 83)).astype(dtype)
+    fn = str(tmp_path / 'in.tif')
+    rasterfile.writeImage(fn, img, nodata=7)
+    src = rasterfile.TiffSource(fn)
+    assert (src.count, src.ysize, src.xsize) == img.shape
+    assert src.dtype == numpy.dtype(dtype)
+    assert src.nodata == [7, 7, 7]
+    win = src.readWindow([1, 3], 10, 20, 30, 15)
+    assert numpy.array_equal(win, img[[0, 2], 20:35, 10:40])
+    full = src.readWindow([1, 2, 3], 0, 0, 83, 57)
+    assert numpy.array_equal(full, img)
+    src.close()
+
+
+def test_tiff_sink_is_readable(tmp_path):
+    fn = str(tmp_path / 'out.tif')
+    sink = rasterfile.createRaster(fn, 40, 30, 'GTiff', [])
+    a = numpy.arange(12, dtype=numpy.uint32).reshape(3, 4) + 5
+    sink.write(a, 7, 9)
+    sink.setNoData(0)
+    sink.writeHistogram(numpy.arange(4, dtype=numpy.float64))
+    sink.close()
+    src = rasterfile.TiffSource(fn)
+    got = src.readWindow([1], 0, 0, 40, 30)[0]
+    want = numpy.zeros((30, 40), dtype=numpy.uint32)
+    want[9:12, 7:11] = a
+    assert numpy.array_equal(got, want)
+    assert src.nodata == [0]
+    assert os.path.exists(fn + '.hist.npy')
+    src.close()
+
+
+def test_npy_source_and_sink(tmp_path):
+    img = numpy.arange(2 * 5 * 6, dtype=numpy.uint16).reshape(2, 5, 6)
+    fn = str(tmp_path / 'a.npy')
+    numpy.save(fn, img)
+    src = rasterfile.openRaster(fn)
+    assert numpy.array_equal(src.readWindow([2], 1, 2, 3, 2)[0], img[1, 2:4, 1:4])
+    out = str(tmp_path / 'b.npy')
+    sink = rasterfile.createRaster(out, 6, 5, 'NPY', [])
+    sink.write(numpy.ones((2, 2), dtype=numpy.uint32), 4, 3)
+    sink.close()
+    assert numpy.load(out)[3:, 4:].sum() == 4
+
+
+def test_tile_layout_matches_reference_layouts():
+    """SURVEY probe A13: the layouts getTilesForFile produces for the benchmark rasters"""
+    for (size, tile, ov, n, last) in ((10980, 4096, 1024, 2, (3072, 7908)), (8000, 4096, 1024, 1, (0, 8000)),
+            (40000, 4096, 1024, 12, (33792, 6208)), (1000, 4096, 1024, 1, (0, 1000)),
+            (700, 256, 64, 2, (192, 508))):
+        ti = tiling.getTilesForFile((size, size), tile, ov)
+        assert (ti.ncols, ti.nrows) == (n, n)
+        assert ti.getTile(n - 1, n - 1)[0::2] == last
+        ref = oracle.getTilesForFile(size, size, tile, ov)
+        assert ref.tiles == ti.tiles
+
+
+def test_mode_by_key():
+    keys = numpy.array([5, 5, 5, 9, 9, 2, 2, 2])
+    vals = numpy.array([7, 3, 7, 1, 4, 6, 8, 6])
+    cnts = numpy.array([2, 4, 2, 1, 1, 1, 5, 1])
+    (k, m) = tiling._modeByKey(keys, vals, cnts)
+    got = dict(zip(k.tolist(), m.tolist()))
+    # 5: value 7 has 4, value 3 has 4 -> smallest (3); 9: tie 1/1 -> 1; 2: 8 has 5
+    assert got == {5: 3, 9: 1, 2: 8}
+
+
+def test_timers():
+    t = timinghooks.Timers()
+    with t.interval('a'):
+        pass
+    with t.interval('a'):
+        pass
+    d = t.makeSummaryDict()
+    assert d['a']['count'] == 2 and d['a']['total'] >= 0
+    import pickle
+    t2 = pickle.loads(pickle.dumps(t))
+    assert len(t2.getDurationsForName('a')) == 2
+
+
+def test_argument_errors():
+    img = numpy.zeros((3, 10, 10), dtype=numpy.uint16)
+    with pytest.raises(tiling.PyShepSegTilingError):
+        tiling.doTiledShepherdSegmentation(img, None, overlapSize=3, outputDriver='MEM')
+    with pytest.raises(tiling.PyShepSegTilingError):
+        tiling.doTiledShepherdSegmentation(img, 'x.kea', outputDriver='NoSuchDriver')
+    with pytest.raises(ValueError):
+        tiling.doTiledShepherdSegmentation(img, None, outputDriver='MEM',
+            concurrencyCfg=tiling.SegmentationConcurrencyConfig(concurrencyType='bogus'))
