@@ -430,6 +430,11 @@ def run_ours(args, wl):
             'cpu_baseline': cpu, 'clocks': clocks,
             'segments_per_scene': int(lastRes[1]),
             'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastRes[0].stageMs.items()),
+            'host_ms_last_step': {
+                'resident': dict((k, round(v['total'] * 1e3, 2)) for (k, v) in
+                    lastRes[0].timings.makeSummaryDict().items()),
+                'e2e': dict((k, round(v['total'] * 1e3, 2)) for (k, v) in
+                    lastE2E[0].timings.makeSummaryDict().items())},
         }
         print(json.dumps(line), flush=True)
 

@@ -538,8 +538,9 @@ class TiledSegmenter(object):
                 leftB = lf.buf[1] + (lf.xsize - ov) * 4
                 leftStride = lf.xsize
         tables = _lib.TileTables()
-        ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, ov, topB, topStride,
-            leftB, leftStride, top, bottom, left, right, ctypes.byref(tables))
+        with self.timings.interval('stitch_tables'):
+            ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, ov, topB, topStride,
+                leftB, leftStride, top, bottom, left, right, ctypes.byref(tables))
         n = int(tables.maxId) + 1
         rank = numpy.empty(n, dtype=numpy.uint32)
         flags = numpy.empty(n, dtype=numpy.uint8)
@@ -547,8 +548,9 @@ class TiledSegmenter(object):
         pairCounts = numpy.empty(int(tables.numPairs), dtype=numpy.uint32)
         ctx.call('ssg_tile_tables_fetch', _lib.ptr(rank), _lib.ptr(flags), _lib.ptr(pairKeys),
             _lib.ptr(pairCounts))
-        (lut, trimmedMax) = resolveTile(tables, rank, flags, pairKeys, pairCounts, offset,
-            None if up is None else up.lut, None if lf is None else lf.lut, self.simple)
+        with self.timings.interval('stitch_resolve'):
+            (lut, trimmedMax) = resolveTile(tables, rank, flags, pairKeys, pairCounts, offset,
+                None if up is None else up.lut, None if lf is None else lf.lut, self.simple)
         tile.lut = lut
         # final ids over the trimmed window, on the device, then to the output raster
         (wr, wc) = (bottom - top, right - left)
