@@ -182,12 +182,14 @@ typedef struct ssg_tile_tables {
  * the labels of the upper / left neighbour under this tile's top `overlap` rows / left
  * `overlap` columns (row strides in elements, so they may point into the neighbour's
  * resident label raster), or NULL on the first tile row / column.  [top,bottom) x
- * [left,right) is the trimmed window (tiling.py:997-1022).  Results stay in the context
- * until the next call; sizes come back in *out. */
+ * [left,right) is the trimmed window (tiling.py:997-1022).  maxIdHint is the largest label of
+ * the tile when the caller knows it (ssg_tile_result.numSegments), 0 to have it searched.
+ * Results stay in the context until the next call; sizes come back in *out. */
 int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
                            int64_t overlap, const uint32_t *topBDev, int64_t topBStride,
                            const uint32_t *leftBDev, int64_t leftBStride, int64_t top,
-                           int64_t bottom, int64_t left, int64_t right, ssg_tile_tables *out);
+                           int64_t bottom, int64_t left, int64_t right, uint32_t maxIdHint,
+                           ssg_tile_tables *out);
 /* rank[maxId+1] (1-based among the numbered segments, 0 otherwise), flags[maxId+1]
  * (SSG_SEG_*), pairKeys[numPairs] ascending, pairCounts[numPairs]; host buffers. */
 int ssg_tile_tables_fetch(ssg_ctx *ctx, uint32_t *rank, uint8_t *flags, uint64_t *pairKeys,

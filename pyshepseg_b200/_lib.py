@@ -82,7 +82,7 @@ SIGNATURES = {
     'ssg_download_labels': (_i, [_vp, _vp]),
     'ssg_resident_labels': (_vp, [_vp]),
     'ssg_tile_tables_device': (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64,
-        _i64, _c.POINTER(TileTables)]),
+        _i64, _u32, _c.POINTER(TileTables)]),
     'ssg_tile_tables_fetch': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'ssg_apply_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _u32, _i64, _i64, _i64, _i64, _vp, _i64,
         _vp, _i64]),

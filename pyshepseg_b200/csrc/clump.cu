@@ -7,8 +7,9 @@
 // LIFO flood fill carves it (shepseg.py:481,502,523-537).
 //
 // How it is done here
-//   1. ccl_local : union-find over a 64x32 pixel block in shared memory (atomicCAS linking to
-//                  the smaller index), roots written as global linear indices;
+//   1. ccl_local : 32x64 pixel blocks; horizontal runs from warp ballots, vertical links by
+//                  union-find in shared memory (atomicCAS linking to the smaller index),
+//                  roots written as global linear indices;
 //   2. ccl_border: unions across block borders in global memory;
 //   3. ccl_flatten: every pixel points at its root = the raster-first pixel of its region,
 //                  which is the reference's seed pixel;
@@ -22,9 +23,10 @@
 
 #include <cub/device/device_scan.cuh>
 
-#define CCL_TW 64
-#define CCL_TH 32
+#define CCL_TW 32          // tile width = one warp
+#define CCL_TH 64
 #define CCL_THREADS 256
+#define CCL_ROWS (CCL_TH / (CCL_THREADS / 32))   // rows walked by a warp
 #define CCL_PIX (CCL_TW * CCL_TH)
 #define SSG_UNVISITED 0xFFFFFFFEu
 #define NUM_BLOCK_PIX 1024   // pixels per numbering block (256 threads x 4 consecutive)
@@ -71,56 +73,93 @@ __device__ __forceinline__ void g_union(unsigned *L, unsigned a, unsigned b)
 }
 
 // ---- 1. block-local labelling --------------------------------------------------------------
+// A block labels a 32 x 64 pixel tile; a warp spans the tile's width and walks 8 rows, so a
+// pixel's left neighbour is the lane below and the pixel above is the previous iteration's
+// register.  Horizontal runs need no union at all: the ballot of "same as the left pixel" gives
+// every lane the start of its run by bit arithmetic, and the run start is the pixel's first
+// label.  Only the vertical links go through the shared-memory union-find, and of those only
+// the first of every stretch where two runs overlap (the rest are implied).
+__device__ __forceinline__ unsigned run_start(unsigned eqLeft, unsigned lane)
+{
+    // highest lane <= mine that does not continue its left neighbour's run
+    return 31u - (unsigned)__clz(~eqLeft & (0xffffffffu >> (31u - lane)));
+}
+
 __global__ void __launch_bounds__(CCL_THREADS)
 k_ccl_local(const int32_t *__restrict__ img, int64_t nRows, int64_t nCols, int32_t ignoreVal,
             int four, unsigned *__restrict__ label)
 {
-    __shared__ int32_t c[CCL_PIX];
     __shared__ unsigned par[CCL_PIX];
-    const int64_t x0 = (int64_t)blockIdx.x * CCL_TW;
-    const int64_t y0 = (int64_t)blockIdx.y * CCL_TH;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int64_t x0 = (int64_t)blockIdx.x * CCL_TW, y0 = (int64_t)blockIdx.y * CCL_TH;
+    const int64_t gx = x0 + lane;
+    const bool colOk = gx < nCols;
+    const unsigned ly0 = warp * CCL_ROWS;
+
+    // the row above this warp's rows, when it is inside the tile (another warp labels it)
+    int32_t upv = ignoreVal;
+    unsigned upEq = 0, upRs = lane;
+    if (ly0 > 0) {
+        const int64_t gy = y0 + ly0 - 1;
+        if (colOk && gy < nRows) upv = __ldg(img + gy * nCols + gx);
+        const int32_t left = __shfl_up_sync(0xffffffffu, upv, 1);
+        upEq = __ballot_sync(0xffffffffu, lane > 0 && upv == left && upv != ignoreVal);
+        upRs = run_start(upEq, lane);
+    }
+
+    int32_t v[CCL_ROWS];
+    unsigned eq[CCL_ROWS], rs[CCL_ROWS];
+#pragma unroll
+    for (int r = 0; r < CCL_ROWS; r++) {
+        const unsigned ly = ly0 + r;
+        const int64_t gy = y0 + ly;
+        int32_t val = ignoreVal;
+        if (colOk && gy < nRows) val = __ldg(img + gy * nCols + gx);
+        const int32_t left = __shfl_up_sync(0xffffffffu, val, 1);
+        eq[r] = __ballot_sync(0xffffffffu, lane > 0 && val == left && val != ignoreVal);
+        rs[r] = run_start(eq[r], lane);
+        v[r] = val;
+        if (rs[r] == lane) par[ly * CCL_TW + lane] = ly * CCL_TW + lane;
+    }
+    __syncthreads();
 
 #pragma unroll
-    for (int m = 0; m < CCL_PIX / CCL_THREADS; m++) {
-        int i = threadIdx.x + m * CCL_THREADS;
-        int64_t gx = x0 + (i % CCL_TW), gy = y0 + (i / CCL_TW);
-        int32_t v = ignoreVal;
-        if (gx < nCols && gy < nRows) v = __ldg(img + gy * nCols + gx);
-        c[i] = v;
-        par[i] = i;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < CCL_PIX / CCL_THREADS; m++) {
-        int i = threadIdx.x + m * CCL_THREADS;
-        int lx = i % CCL_TW, ly = i / CCL_TW;
-        int32_t v = c[i];
-        if (v == ignoreVal) continue;
-        bool left = lx > 0 && c[i - 1] == v;
-        bool up = ly > 0 && c[i - CCL_TW] == v;
-        if (left) s_union(par, i, i - 1);
-        if (up) {
-            // when left, up-left and up are all the same value the up link is implied by
-            // the row above's own left link
-            bool implied = left && c[i - CCL_TW - 1] == v;
-            if (!implied) s_union(par, i, i - CCL_TW);
-        }
-        if (!four && ly > 0) {
+    for (int r = 0; r < CCL_ROWS; r++) {
+        const unsigned ly = ly0 + r;
+        if (ly == 0) continue;     // the tile's first row: the border kernel links it upwards
+        const int32_t up = r == 0 ? upv : v[r > 0 ? r - 1 : 0];
+        const unsigned pe = r == 0 ? upEq : eq[r > 0 ? r - 1 : 0];
+        const unsigned prs = r == 0 ? upRs : rs[r > 0 ? r - 1 : 0];
+        const bool valid = v[r] != ignoreVal;
+        const unsigned eu = __ballot_sync(0xffffffffu, valid && v[r] == up);
+        const unsigned mine = ly * CCL_TW + rs[r];
+        // lane x is implied when x-1 is linked upwards too and both rows continue a run there
+        const unsigned need = eu & ~((eu << 1) & eq[r] & pe);
+        if ((need >> lane) & 1u) s_union(par, mine, (ly - 1) * CCL_TW + prs);
+        if (!four) {
             // diagonals matter only when the orthogonal neighbours do not already connect
-            if (lx > 0 && c[i - CCL_TW - 1] == v && !left && !up) s_union(par, i, i - CCL_TW - 1);
-            if (lx < CCL_TW - 1 && c[i - CCL_TW + 1] == v && !up) s_union(par, i, i - CCL_TW + 1);
+            const int32_t ul = __shfl_up_sync(0xffffffffu, up, 1);
+            const int32_t ur = __shfl_down_sync(0xffffffffu, up, 1);
+            const unsigned prsL = __shfl_up_sync(0xffffffffu, prs, 1);
+            const unsigned prsR = __shfl_down_sync(0xffffffffu, prs, 1);
+            const bool left = (eq[r] >> lane) & 1u, upSame = (eu >> lane) & 1u;
+            if (lane > 0 && valid && v[r] == ul && !left && !upSame)
+                s_union(par, mine, (ly - 1) * CCL_TW + prsL);
+            if (lane < 31 && valid && v[r] == ur && !upSame)
+                s_union(par, mine, (ly - 1) * CCL_TW + prsR);
         }
     }
     __syncthreads();
+
 #pragma unroll
-    for (int m = 0; m < CCL_PIX / CCL_THREADS; m++) {
-        int i = threadIdx.x + m * CCL_THREADS;
-        int64_t gx = x0 + (i % CCL_TW), gy = y0 + (i / CCL_TW);
-        if (gx >= nCols || gy >= nRows) continue;
+    for (int r = 0; r < CCL_ROWS; r++) {
+        const unsigned ly = ly0 + r;
+        const int64_t gy = y0 + ly;
+        if (!colOk || gy >= nRows) continue;
         unsigned out = SSG_NIL;
-        if (c[i] != ignoreVal) {
-            unsigned r = s_find(par, i);
-            out = (unsigned)((y0 + r / CCL_TW) * nCols + x0 + (r % CCL_TW));
+        if (v[r] != ignoreVal) {
+            const unsigned root = s_find(par, ly * CCL_TW + rs[r]);
+            out = (unsigned)((y0 + root / CCL_TW) * nCols + x0 + (root % CCL_TW));
         }
         label[gy * nCols + gx] = out;
     }

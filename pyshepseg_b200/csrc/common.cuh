@@ -74,14 +74,10 @@ enum Counter {
     C_NUM_MOVES,
     C_NUM_LEFT,
     C_NUM_ALIVE,
+    C_NUM_SMALLSEG,
     C_NUM_SMALLPIX,
     C_NUM_BIGSUM,
     C_NUM_ELIM,
-    C_NUM_CAND0,
-    C_NUM_CAND1,
-    C_NUM_TARGETS0,
-    C_NUM_TARGETS1,
-    C_NUM_PASSES,
     C_MAXLABEL,
     C_SCRATCH0,
     C_SCRATCH1,

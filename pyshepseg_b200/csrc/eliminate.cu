@@ -361,20 +361,60 @@ static int build_spectra_t(ssg_ctx *ctx, const T *img, int nB, int64_t N, const 
 }
 
 // ====================================================================================
-// pixel lists of the small segments (makeSegmentLocations, shepseg.py:880-915)
+// pixel lists and size buckets of the small segments (makeSegmentLocations, shepseg.py:880-915)
 // ====================================================================================
+#define SMALL_MAX_MINSEG 8192   // size-histogram bins kept in shared memory
+
+// per segment: listed pixel count (its size if 0 < size < minSegSize) for the chunk-offset
+// scan, the histogram of those sizes, and the totals
 __global__ void __launch_bounds__(256)
-k_list_counts(const unsigned *__restrict__ segSize, int64_t len, unsigned minSegSize,
-              unsigned *cnt /* len + 1 */)
+k_small_census(const unsigned *__restrict__ segSize, int64_t len, unsigned minSegSize,
+               unsigned *cnt /* len + 1 */, unsigned *sizeHist /* minSegSize + 1 */,
+               unsigned long long *counters)
 {
+    extern __shared__ unsigned hist[];
+    for (unsigned i = threadIdx.x; i < minSegSize; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > len) return;
     unsigned c = 0;
     if (s >= 1 && s < len) {
-        unsigned z = segSize[s];
+        const unsigned z = segSize[s];
         if (z > 0 && z < minSegSize) c = z;
     }
-    cnt[s] = c;
+    if (s <= len) cnt[s] = c;
+    if (c) atomicAdd(&hist[c], 1u);
+    const unsigned m = __ballot_sync(0xffffffffu, c != 0);
+    const unsigned pixTot = __reduce_add_sync(0xffffffffu, c);
+    if (lane_id() == 0 && m) {
+        atomicAdd(&counters[C_NUM_SMALLSEG], (unsigned long long)__popc(m));
+        atomicAdd(&counters[C_NUM_SMALLPIX], (unsigned long long)pixTot);
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < minSegSize; i += blockDim.x)
+        if (hist[i]) atomicAdd(&sizeHist[i], hist[i]);
+}
+
+// the small segments grouped by size: bucketList[bucketStart[z] ..) holds the ids of size z
+__global__ void __launch_bounds__(256)
+k_bucket_fill(const unsigned *__restrict__ segSize, int64_t len, unsigned minSegSize,
+              const unsigned *__restrict__ bucketStart, unsigned *bucketFill, unsigned *bucketList)
+{
+    extern __shared__ unsigned sh[];
+    unsigned *hist = sh, *base = sh + minSegSize;
+    for (unsigned i = threadIdx.x; i < minSegSize; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned z = 0, myRank = 0;
+    if (s >= 1 && s < len) {
+        z = segSize[s];
+        if (z >= minSegSize) z = 0;
+    }
+    if (z) myRank = atomicAdd(&hist[z], 1u);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < minSegSize; i += blockDim.x)
+        if (hist[i]) base[i] = bucketStart[i] + atomicAdd(&bucketFill[i], hist[i]);
+    __syncthreads();
+    if (z) bucketList[base[z] + myRank] = (unsigned)s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -393,11 +433,14 @@ k_list_fill(const unsigned *__restrict__ seg, int64_t N, const unsigned *__restr
 
 // slots were claimed in arbitrary order: put every list back into raster order
 __global__ void __launch_bounds__(128)
-k_list_sort(const unsigned *__restrict__ off, int64_t len, unsigned *pix, unsigned *nextChunk,
-            unsigned *tailChunk, unsigned *mergeTo, unsigned *pendHead)
+k_list_sort(const unsigned *__restrict__ off, int64_t len, unsigned *pix, unsigned *sliceOff,
+            unsigned *sliceLen, unsigned *nextChunk, unsigned *tailChunk, unsigned *mergeTo,
+            unsigned *pendHead)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= len) return;
+    sliceOff[s] = off[s];
+    sliceLen[s] = off[s + 1] - off[s];
     nextChunk[s] = SSG_NIL;
     tailChunk[s] = (unsigned)s;
     mergeTo[s] = 0;
@@ -414,17 +457,48 @@ k_list_sort(const unsigned *__restrict__ off, int64_t len, unsigned *pix, unsign
 // ====================================================================================
 // small-segment passes
 // ====================================================================================
+// Counters of the persistent kernel; all of them only ever grow (lists are ranges of rings).
+// The three that a find phase appends to exist twice, indexed by the parity of the phase
+// number: a find phase may follow another find phase directly, and the blocks that leave the
+// barrier first would otherwise move the counters the slower blocks are still reading.
+enum SmallCtr {
+    SF_TARGETS = 0,   // targets registered by a find phase
+    SF_NEXT,          // candidates a find phase left unmerged
+    SF_SELECT,        // grown segments selected for the next size
+    SF_COUNT = 4,
+    SC_GROWN = 8,     // entries of grownLog            (apply phases)
+    SC_ARENA,         // pixels handed out by the arena  (apply phases)
+    SC_ELIM,          // merges done
+    SC_PASSES,
+    SC_COUNT = 16
+};
+
+struct SmallBarrier {
+    unsigned arrive;
+    unsigned pad[31];
+};
+
 struct SmallState {
     unsigned *seg;
     unsigned *segSize;
     float *fsum;
-    const unsigned *off;      // len+1: pixel-array slice of every original small segment
-    const unsigned *pix;
-    unsigned *nextChunk, *tailChunk;
+    const unsigned *off;      // len+1: initial pixel slice of every segment (empty unless small)
+    unsigned *pix;            // [0, numSmallPix): initial lists; then the arena of merged lists
+    unsigned *sliceOff, *sliceLen;   // current pixel slice of every list node
+    unsigned *nextChunk, *tailChunk; // list = chain of slices (one slice unless the arena ran out)
     unsigned *mergeTo;
     unsigned *pendHead, *pendNext;
-    unsigned *cand, *targets;
-    unsigned long long *counters;
+    const unsigned *bucketStart;   // minSegSize+1
+    const unsigned *bucketList;    // the initially small segments grouped by size
+    unsigned *targets[2];          // rings of cap entries, per phase parity
+    unsigned *nextList[2];         // rings of 2*cap entries
+    unsigned *selList[2];          // cap entries
+    unsigned long long *grownLog;  // cap entries: size << 32 | id of targets that grew but stayed small
+    unsigned long long *ctr;       // [2][SF_COUNT] parity sets, then the SC_* counters
+    SmallBarrier *bar;
+    unsigned long long *dbg;       // optional: cycles per phase kind, written by thread 0
+    unsigned cap;                  // number of initially small segments
+    unsigned arenaBase, arenaCap;  // arena = pix[arenaBase, arenaBase + arenaCap)
     int nB;
     int64_t nRows, nCols;
     int four;
@@ -448,39 +522,79 @@ __device__ __forceinline__ unsigned group_width(int t)
     return g;
 }
 
-// phase 0: list the segments whose size is exactly t (order irrelevant)
-__device__ void phase_enum(const SmallState &st, unsigned t, int par, int64_t gtid, int64_t gsize)
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 {
-    const int64_t n = ((int64_t)st.len + 31) / 32 * 32;   // warp-uniform trip count
-    for (int64_t s = gtid; s < n; s += gsize) {
-        bool hit = s >= 1 && s < st.len && st.segSize[s] == t;
-        unsigned long long slot = warp_claim(&st.counters[C_NUM_CAND0 + par], hit);
-        if (hit) st.cand[slot] = (unsigned)s;
-    }
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-// phase 1: findMergeSegment (shepseg.py:1003-1063) for every candidate, state frozen.
-// A sub-warp of G lanes walks the candidate's chunk chain; lane l takes every G-th pixel of a
-// chunk.  The first strict minimum in (list position, neighbour scan order) wins.
+// Grid-wide barrier (the kernel is launched cooperatively, so every block is resident).  On the
+// way out every block picks up the find-phase counters of parity `set` for all its threads.
+__device__ __forceinline__ void small_barrier(const SmallState &st, unsigned &phase, int set,
+                                              unsigned long long *curSh)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned target = (phase + 1) * gridDim.x;
+        __threadfence();
+        atomicAdd(&st.bar->arrive, 1u);
+        while (ld_acquire_u32(&st.bar->arrive) < target) { }
+#pragma unroll
+        for (int i = 0; i < SF_COUNT; i++)
+            curSh[i] = *(volatile unsigned long long *)&st.ctr[set * SF_COUNT + i];
+    }
+    phase++;
+    __syncthreads();
+}
+
+// where the candidates of a pass come from: pass 1 of a size reads the size's bucket followed by
+// the selected grown segments (either may hold segments that have grown since: validated
+// against segSize); later passes read the previous pass's unmerged candidates
+struct CandSource {
+    const unsigned *a; unsigned na;
+    const unsigned *b; unsigned long long b0; unsigned nb; unsigned bCap;
+    const unsigned *ring; unsigned long long r0; unsigned nr; unsigned ringCap;
+    __device__ __forceinline__ unsigned count() const { return na + nb + nr; }
+    __device__ __forceinline__ unsigned at(unsigned i) const
+    {
+        if (i < na) return a[i];
+        i -= na;
+        if (i < nb) return b[(b0 + i) % bCap];
+        i -= nb;
+        return ring[(r0 + i) % ringCap];
+    }
+};
+
+// findMergeSegment (shepseg.py:1003-1063) for every candidate, state frozen.  A sub-warp of G
+// lanes walks the candidate's pixel list; lane l takes every G-th pixel of a slice.  The first
+// strict minimum in (list position, neighbour scan order) wins.
 template <int NBMAX>
-__device__ void phase_find(const SmallState &st, unsigned t, int par, int64_t gtid, int64_t gsize)
+__device__ void phase_find(const SmallState &st, unsigned t, const CandSource &src, int set,
+                           int64_t gtid, int64_t gsize)
 {
     const unsigned G = group_width((int)t);
-    const unsigned nCand = (unsigned)*(volatile unsigned long long *)&st.counters[C_NUM_CAND0 + par];
+    const unsigned nCand = src.count();
     const unsigned lane = lane_id();
     const unsigned sub = lane % G;
     const unsigned groupsPerWarp = 32u / G;
     const int64_t warpId = gtid >> 5, nWarps = gsize >> 5;
     const int nB = st.nB;
+    const unsigned nextCap = 2u * st.cap;
+    unsigned long long *ctrF = st.ctr + set * SF_COUNT;
+    unsigned *targets = st.targets[set], *nextList = st.nextList[set];
 
     for (int64_t c0 = warpId * groupsPerWarp; c0 < (int64_t)nCand; c0 += nWarps * groupsPerWarp) {
         const int64_t c = c0 + lane / G;
-        const bool active = c < (int64_t)nCand;
+        bool active = c < (int64_t)nCand;
         unsigned long long bestKey = ~0ull;
         unsigned bestU = 0;
         unsigned s = 0;
         if (active) {
-            s = st.cand[c];
+            s = src.at((unsigned)c);
+            active = st.segSize[s] == t;      // a listed segment may have grown since
+        }
+        if (active) {
             float ms[NBMAX];
 #pragma unroll
             for (int b = 0; b < NBMAX; b++)
@@ -489,7 +603,7 @@ __device__ void phase_find(const SmallState &st, unsigned t, int par, int64_t gt
             unsigned lastU = 0;
             float lastD = 0.0f;
             for (unsigned ch = s; ch != SSG_NIL; ch = st.nextChunk[ch]) {
-                const unsigned o = st.off[ch], n = st.off[ch + 1] - o;
+                const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
                 for (unsigned i = sub; i < n; i += G) {
                     const unsigned p = st.pix[o + i];
                     const unsigned k = posBase + i;
@@ -537,175 +651,268 @@ __device__ void phase_find(const SmallState &st, unsigned t, int par, int64_t gt
             unsigned ou = __shfl_xor_sync(0xffffffffu, bestU, o);
             if (ok < bestKey) { bestKey = ok; bestU = ou; }
         }
-        if (active && sub == 0 && bestKey != ~0ull) {
+        // one lane per candidate records the decision; list slots are claimed once per warp
+        bool merged = false;
+        const bool leader = active && sub == 0;
+        if (leader && bestKey != ~0ull) {
             const float d = __uint_as_float((unsigned)(bestKey >> 32));
-            if (!((double)d > st.thr)) {       // shepseg.py:1060
-                st.mergeTo[s] = bestU;
-                const unsigned old = atomicExch(&st.pendHead[bestU], s);
-                st.pendNext[s] = old;
-                if (old == 0) {
-                    unsigned long long slot = atomicAdd(&st.counters[C_NUM_TARGETS0 + par], 1ull);
-                    st.targets[slot] = bestU;
-                }
-            }
+            merged = !((double)d > st.thr);       // shepseg.py:1060
         }
+        bool newTarget = false;
+        if (merged) {
+            st.mergeTo[s] = bestU;
+            const unsigned old = atomicExch(&st.pendHead[bestU], s);
+            st.pendNext[s] = old;
+            newTarget = old == 0;
+        }
+        const unsigned long long tslot = warp_claim(&ctrF[SF_TARGETS], newTarget);
+        if (newTarget) targets[tslot % st.cap] = bestU;
+        // still of size t after this pass: a candidate of the next one
+        const bool again = leader && !merged;
+        const unsigned long long nslot = warp_claim(&ctrF[SF_NEXT], again);
+        if (again) nextList[nslot % nextCap] = s;
     }
 }
 
-// phase 2: seg[pixels of source] = target (first half of doMerge, shepseg.py:1107-1110)
-__device__ void phase_relabel(const SmallState &st, unsigned t, int par, int64_t gtid, int64_t gsize)
+// The grown segments that have exactly `size` pixels -> selList of parity `set`.  Every log
+// entry of that size exists before the passes of size-1 start (a merge at target size t makes
+// segments of at least 2t+1 pixels), so this can ride along with any phase of size-1; an entry
+// whose segment grows further in the meantime is dropped when the list is used.
+__device__ void phase_select(const SmallState &st, unsigned size, int set, int64_t gtid, int64_t gsize)
+{
+    const unsigned long long nGrown = *(volatile unsigned long long *)&st.ctr[SC_GROWN];
+    const int64_t n = ((int64_t)nGrown + 31) / 32 * 32;   // warp-uniform trip count
+    for (int64_t i = gtid; i < n; i += gsize) {
+        bool hit = false;
+        unsigned s = 0;
+        if (i < (int64_t)nGrown) {
+            const unsigned long long e = st.grownLog[i];
+            s = (unsigned)e;
+            hit = (unsigned)(e >> 32) == size && st.segSize[s] == size;
+        }
+        const unsigned long long slot = warp_claim(&st.ctr[set * SF_COUNT + SF_SELECT], hit);
+        if (hit) st.selList[set][slot % st.cap] = s;
+    }
+}
+
+// seg[pixels of source] = target (first half of doMerge, shepseg.py:1107-1110)
+__device__ void phase_relabel(const SmallState &st, unsigned t, const CandSource &src,
+                              int64_t gtid, int64_t gsize)
 {
     const unsigned G = group_width((int)t);
-    const unsigned nCand = (unsigned)*(volatile unsigned long long *)&st.counters[C_NUM_CAND0 + par];
+    const unsigned nCand = src.count();
     const unsigned sub = lane_id() % G;
     const int64_t groupId = gtid / G, nGroups = gsize / G;
     for (int64_t c = groupId; c < (int64_t)nCand; c += nGroups) {
-        const unsigned s = st.cand[c];
+        const unsigned s = src.at((unsigned)c);
         const unsigned u = st.mergeTo[s];
         if (u == 0) continue;
         for (unsigned ch = s; ch != SSG_NIL; ch = st.nextChunk[ch]) {
-            const unsigned o = st.off[ch], n = st.off[ch + 1] - o;
+            const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
             for (unsigned i = sub; i < n; i += G) st.seg[st.pix[o + i]] = u;
         }
     }
 }
 
-// phase 3: per target, its sources in ascending id (shepseg.py:989-994): float32 sum adds,
-// size add, chain append (second half of doMerge, shepseg.py:1099-1123)
-__device__ void phase_apply(const SmallState &st, int par, int64_t gtid, int64_t gsize)
+// Per target, its sources in ascending id (shepseg.py:989-994): float32 sum adds, size add, and
+// the new pixel list = the target's list followed by the sources' lists (second half of doMerge,
+// shepseg.py:1099-1123).  Only a target that is still small afterwards will have its list walked
+// again; it gets a fresh contiguous slice from the arena (a later find then reads one slice, not
+// a chain of them).  If the arena is exhausted the slices are chained instead.
+#define APPLY_SORT_MAX 24
+__device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *targets,
+                            unsigned long long t0, unsigned nT, int64_t gtid, int64_t gsize)
 {
-    const unsigned nT = (unsigned)*(volatile unsigned long long *)&st.counters[C_NUM_TARGETS0 + par];
     const int nB = st.nB;
     unsigned long long merged = 0;
     for (int64_t i = gtid; i < (int64_t)nT; i += gsize) {
-        const unsigned u = st.targets[i];
-        const bool listed = st.off[u + 1] != st.off[u];
+        const unsigned u = targets[(t0 + i) % st.cap];
+        unsigned ids[APPLY_SORT_MAX];
+        unsigned k = 0;
+        for (unsigned s = st.pendHead[u]; s != 0; s = st.pendNext[s]) {
+            if (k < APPLY_SORT_MAX) {
+                unsigned j = k;
+                while (j > 0 && ids[j - 1] > s) { ids[j] = ids[j - 1]; j--; }
+                ids[j] = s;
+            }
+            k++;
+        }
+        const unsigned oldSize = st.segSize[u];
+        const unsigned newSize = oldSize + k * t;      // every source has exactly t pixels
+        const bool keepList = newSize < (unsigned)st.minSegSize;   // then u was small all along
+        unsigned dst = SSG_NIL, w = 0;
+        if (keepList) {
+            const unsigned long long a = atomicAdd(&st.ctr[SC_ARENA], (unsigned long long)newSize);
+            if (a + newSize <= st.arenaCap) {
+                dst = st.arenaBase + (unsigned)a;
+                for (unsigned ch = u; ch != SSG_NIL; ch = st.nextChunk[ch]) {
+                    const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
+                    for (unsigned q = 0; q < n; q++) st.pix[dst + w++] = st.pix[o + q];
+                }
+            }
+        }
         unsigned last = 0;   // ids are >= 1
-        while (true) {
-            // smallest pending source with id > last
-            unsigned nxt = SSG_NIL;
-            for (unsigned s = st.pendHead[u]; s != 0; s = st.pendNext[s])
-                if (s > last && s < nxt) nxt = s;
-            if (nxt == SSG_NIL) break;
-            const unsigned s = nxt;
+        for (unsigned m = 0; m < k; m++) {
+            unsigned s;
+            if (k <= APPLY_SORT_MAX) s = ids[m];
+            else {           // long lists: smallest pending source with id > last
+                s = SSG_NIL;
+                for (unsigned q = st.pendHead[u]; q != 0; q = st.pendNext[q])
+                    if (q > last && q < s) s = q;
+            }
             for (int b = 0; b < nB; b++) {
                 float *tu = &st.fsum[(size_t)u * nB + b];
                 float *ts = &st.fsum[(size_t)s * nB + b];
                 *tu = __fadd_rn(*tu, *ts);
                 *ts = 0.0f;
             }
-            st.segSize[u] += st.segSize[s];
             st.segSize[s] = 0;
-            if (listed) {
-                st.nextChunk[st.tailChunk[u]] = s;
-                st.tailChunk[u] = st.tailChunk[s];
+            if (keepList) {
+                if (dst != SSG_NIL) {
+                    for (unsigned ch = s; ch != SSG_NIL; ch = st.nextChunk[ch]) {
+                        const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
+                        for (unsigned q = 0; q < n; q++) st.pix[dst + w++] = st.pix[o + q];
+                    }
+                } else {
+                    st.nextChunk[st.tailChunk[u]] = s;
+                    st.tailChunk[u] = st.tailChunk[s];
+                }
             }
-            st.mergeTo[s] = 0;
-            merged++;
             last = s;
         }
+        st.segSize[u] = newSize;
         st.pendHead[u] = 0;
+        merged += k;
+        if (keepList) {
+            if (dst != SSG_NIL) {
+                st.sliceOff[u] = dst;
+                st.sliceLen[u] = newSize;
+                st.nextChunk[u] = SSG_NIL;
+                st.tailChunk[u] = u;
+            }
+            // it will be a candidate itself at that size
+            const unsigned long long slot = atomicAdd(&st.ctr[SC_GROWN], 1ull);
+            st.grownLog[slot] = ((unsigned long long)newSize << 32) | u;
+        }
     }
-    if (merged) atomicAdd(&st.counters[C_NUM_ELIM], merged);
+    if (merged) atomicAdd(&st.ctr[SC_ELIM], merged);
 }
 
-// The targetSize loop of eliminateSmallSegments (shepseg.py:970-997) as one cooperative kernel.
+#define DBG_TICK(slot)                                                   \
+    do {                                                                 \
+        if (dbgOn) {                                                     \
+            const long long now = clock64();                             \
+            dbgAcc[slot] += (unsigned long long)(now - dbgLast);         \
+            dbgCnt[slot]++;                                              \
+            dbgLast = now;                                               \
+        }                                                                \
+    } while (0)
+
+// The targetSize loop of eliminateSmallSegments (shepseg.py:970-997) as one persistent kernel.
+// Per pass: find | barrier | relabel + apply | barrier.  The reference stops a size when a pass
+// leaves the number of segments of that size unchanged (shepseg.py:980,996), i.e. when a pass
+// merged nothing; the candidates of pass p+1 are exactly the unmerged candidates of pass p
+// (merging only creates sizes larger than the current one).
 template <int NBMAX>
 __global__ void __launch_bounds__(256)
 k_small_persistent(SmallState st)
 {
-    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long cur[SF_COUNT];
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
-    int par = 0;
+    const bool dbgOn = st.dbg != nullptr && gtid == 0;
+    unsigned long long dbgAcc[6] = {0, 0, 0, 0, 0, 0}, dbgCnt[6] = {0, 0, 0, 0, 0, 0};
+    long long dbgLast = clock64();
+    unsigned phase = 0;
+    unsigned long long base[2][SF_COUNT] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // the host zeroes the counters
     unsigned long long passes = 0;
+    int selSet = 0;
+    unsigned long long selLo = 0, selHi = 0;   // selList[selSet] range: the grown segments of size t
     for (int t = 1; t < st.minSegSize; t++) {
-        long long prev = -1;
+        CandSource src;
+        src.a = st.bucketList + st.bucketStart[t];
+        src.na = st.bucketStart[t + 1] - st.bucketStart[t];
+        src.b = st.selList[selSet]; src.b0 = selLo; src.nb = (unsigned)(selHi - selLo); src.bCap = st.cap;
+        src.ring = nullptr; src.r0 = 0; src.nr = 0; src.ringCap = 2u * st.cap;
+        bool needSelect = t + 1 < st.minSegSize;   // the list of size t+1 rides on the first phase
         int numPasses = 0;
-        while (true) {
-            phase_enum(st, (unsigned)t, par, gtid, gsize);
-            grid.sync();
-            const long long count = (long long)*(volatile unsigned long long *)&st.counters[C_NUM_CAND0 + par];
-            if (gtid == 0) {   // the other parity's counters are idle now: clear them for the next pass
-                st.counters[C_NUM_CAND0 + (par ^ 1)] = 0;
-                st.counters[C_NUM_TARGETS0 + (par ^ 1)] = 0;
+        while (src.count() > 0) {
+            const int set = (int)(phase & 1u);
+            phase_find<NBMAX>(st, (unsigned)t, src, set, gtid, gsize);
+            if (needSelect) phase_select(st, (unsigned)t + 1, set, gtid, gsize);
+            DBG_TICK(0);
+            small_barrier(st, phase, set, cur);
+            DBG_TICK(1);
+            const unsigned long long tg0 = base[set][SF_TARGETS], nx0 = base[set][SF_NEXT];
+            const unsigned nT = (unsigned)(cur[SF_TARGETS] - tg0);
+            const unsigned nNext = (unsigned)(cur[SF_NEXT] - nx0);
+            if (needSelect) {
+                selSet = set; selLo = base[set][SF_SELECT]; selHi = cur[SF_SELECT];
+                needSelect = false;
             }
-            if (count == prev || numPasses >= 10 || count == 0) { par ^= 1; grid.sync(); break; }
-            prev = count;
-            phase_find<NBMAX>(st, (unsigned)t, par, gtid, gsize);
-            grid.sync();
-            phase_relabel(st, (unsigned)t, par, gtid, gsize);
-            grid.sync();
-            phase_apply(st, par, gtid, gsize);
-            par ^= 1;
+#pragma unroll
+            for (int i = 0; i < SF_COUNT; i++) base[set][i] = cur[i];
             numPasses++;
             passes++;
-            grid.sync();
+            if (nT == 0) break;      // nothing merged: the count of this size is unchanged
+            phase_relabel(st, (unsigned)t, src, gtid, gsize);
+            phase_apply(st, (unsigned)t, st.targets[set], tg0, nT, gtid, gsize);
+            DBG_TICK(2);
+            small_barrier(st, phase, set, cur);    // (the find counters did not move)
+            DBG_TICK(3);
+            if (numPasses >= 10) break;       // shepseg.py:980
+            src.na = 0; src.nb = 0;
+            src.ring = st.nextList[set]; src.r0 = nx0; src.nr = nNext;
+        }
+        if (needSelect) {            // no find phase ran for this size
+            const int set = (int)(phase & 1u);
+            phase_select(st, (unsigned)t + 1, set, gtid, gsize);
+            DBG_TICK(4);
+            small_barrier(st, phase, set, cur);
+            DBG_TICK(5);
+            selSet = set; selLo = base[set][SF_SELECT]; selHi = cur[SF_SELECT];
+#pragma unroll
+            for (int i = 0; i < SF_COUNT; i++) base[set][i] = cur[i];
+        } else if (t + 1 >= st.minSegSize) {
+            selLo = selHi = 0;
         }
     }
-    if (gtid == 0) st.counters[C_NUM_PASSES] = passes;
-}
-
-// the same phases as separate launches, driven from the host (debugging / comparison)
-template <int NBMAX>
-__global__ void __launch_bounds__(256) k_phase(SmallState st, int phase, unsigned t, int par)
-{
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
-    if (phase == 0) phase_enum(st, t, par, gtid, gsize);
-    else if (phase == 1) phase_find<NBMAX>(st, t, par, gtid, gsize);
-    else if (phase == 2) phase_relabel(st, t, par, gtid, gsize);
-    else phase_apply(st, par, gtid, gsize);
+    if (gtid == 0) st.ctr[SC_PASSES] = passes;
+    if (dbgOn)
+        for (int i = 0; i < 6; i++) { st.dbg[i] = dbgAcc[i]; st.dbg[6 + i] = dbgCnt[i]; }
 }
 
 template <int NBMAX>
-static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses)
+static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses, int64_t *numElim)
 {
-    unsigned long long *counters = st.counters;
-    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_ELIM, 0, (C_NUM_PASSES - C_NUM_ELIM + 1) * sizeof(unsigned long long), ctx->stream));
-    const char *mode = getenv("SSG_SMALL_MODE");
-    const bool hostLoop = mode && strcmp(mode, "host") == 0;
-    if (!hostLoop) {
-        int perSM = 0;
-        SSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_small_persistent<NBMAX>, 256, 0));
-        if (perSM < 1) SSG_FAIL(ctx, SSG_ERR_CUDA, "persistent merge kernel does not fit on an SM");
-        if (perSM > 4) perSM = 4;
-        dim3 grid((unsigned)(ctx->numSMs * perSM)), block(256);
-        void *args[] = {&st};
-        SSG_PROF_BEGIN(ctx, "k_small_persistent");
-        SSG_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_small_persistent<NBMAX>, grid, block, args, 0, ctx->stream));
-        SSG_LAUNCHED(ctx);
-        SSG_TRY(ssg_fetch_counters(ctx));
-        *numPasses = (uint32_t)ctx->hostCounters[C_NUM_PASSES];
-        return SSG_OK;
+    SSG_CUDA(ctx, cudaMemsetAsync(st.ctr, 0, SC_COUNT * sizeof(unsigned long long) + sizeof(SmallBarrier), ctx->stream));
+    int perSM = 0;
+    SSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_small_persistent<NBMAX>, 256, 0));
+    if (perSM < 1) SSG_FAIL(ctx, SSG_ERR_CUDA, "persistent merge kernel does not fit on an SM");
+    int want = 2;
+    if (const char *e = getenv("SSG_SMALL_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
+    if (perSM > want) perSM = want;
+    dim3 grid((unsigned)(ctx->numSMs * perSM)), block(256);
+    void *args[] = {&st};
+    SSG_PROF_BEGIN(ctx, "k_small_persistent");
+    SSG_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_small_persistent<NBMAX>, grid, block, args, 0, ctx->stream));
+    SSG_LAUNCHED(ctx);
+    uint64_t *host = ctx->hostCounters;   // the pinned mirror doubles as the landing zone
+    SSG_CUDA(ctx, cudaMemcpyAsync(host, st.ctr, SC_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *numPasses = (uint32_t)host[SC_PASSES];
+    *numElim = (int64_t)host[SC_ELIM];
+    if (st.dbg) {
+        unsigned long long d[12];
+        SSG_CUDA(ctx, cudaMemcpy(d, st.dbg, sizeof(d), cudaMemcpyDeviceToHost));
+        static const char *names[6] = {"find+select", "barrier", "relabel+apply", "barrier", "select", "barrier"};
+        for (int i = 0; i < 6; i++)
+            fprintf(stderr, "  small phase %-14s n=%5llu  %8.1f us total  %6.2f us each\n", names[i], d[6 + i],
+                    d[i] / 1965.0, d[6 + i] ? d[i] / 1965.0 / d[6 + i] : 0.0);
+        fprintf(stderr, "  small: %llu small segments, %llu arena pixels of %u, %llu grown\n",
+                (unsigned long long)st.cap, (unsigned long long)host[SC_ARENA], st.arenaCap,
+                (unsigned long long)host[SC_GROWN]);
     }
-    const unsigned grid = (unsigned)ctx->numSMs * 4;
-    int par = 0;
-    uint32_t passes = 0;
-    for (int t = 1; t < st.minSegSize; t++) {
-        long long prev = -1;
-        int np = 0;
-        while (true) {
-            SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_CAND0 + par, 0, sizeof(unsigned long long), ctx->stream));
-            SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_TARGETS0 + par, 0, sizeof(unsigned long long), ctx->stream));
-            SSG_PROF_BEGIN(ctx, "k_phase");
-            k_phase<NBMAX><<<grid, 256, 0, ctx->stream>>>(st, 0, (unsigned)t, par);
-            SSG_LAUNCHED(ctx);
-            SSG_TRY(ssg_fetch_counters(ctx));
-            const long long count = (long long)ctx->hostCounters[C_NUM_CAND0 + par];
-            if (count == prev || np >= 10 || count == 0) break;
-            prev = count;
-            for (int ph = 1; ph <= 3; ph++) {
-                SSG_PROF_BEGIN(ctx, "k_phase");
-                k_phase<NBMAX><<<grid, 256, 0, ctx->stream>>>(st, ph, (unsigned)t, par);
-                SSG_LAUNCHED(ctx);
-            }
-            np++;
-            passes++;
-        }
-    }
-    SSG_TRY(ssg_fetch_counters(ctx));
-    *numPasses = passes;
     return SSG_OK;
 }
 
@@ -719,59 +926,103 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     *numElim = 0;
     *numPasses = 0;
     if (N == 0 || minSegSize <= 1) return SSG_OK;   // the targetSize loop never runs (shepseg.py:970)
+    if (minSegSize > SMALL_MAX_MINSEG)
+        SSG_FAIL(ctx, SSG_ERR_ARG, "minSegmentSize=%d is above the supported maximum of %d", minSegSize, SMALL_MAX_MINSEG);
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
 
     SSG_TRY(build_spectra_t<T>(ctx, img, nB, N, seg, segSize, len));
 
-    // chunk offsets: exclusive scan of the listed sizes, len+1 entries
-    SSG_TRY(ssg_reserve(ctx, ctx->listOff, (size_t)(len + 1) * sizeof(unsigned)));
+    // census of the small segments: listed sizes (-> slice offsets) and the size histogram
+    // (-> buckets); both scans share one scratch array: [off: len+1][hist: m+1][start: m+1][fill: m+1]
+    const size_t m1 = (size_t)minSegSize + 1;
+    SSG_TRY(ssg_reserve(ctx, ctx->listOff, ((size_t)(len + 1) + 3 * m1) * sizeof(unsigned)));
     unsigned *off = bufp<unsigned>(ctx->listOff);
-    SSG_PROF_BEGIN(ctx, "k_list_counts");
-    k_list_counts<<<gridFor(len + 1, 256), 256, 0, ctx->stream>>>(segSize, len, (unsigned)minSegSize, off);
+    unsigned *sizeHist = off + (len + 1), *bucketStart = sizeHist + m1, *bucketFill = bucketStart + m1;
+    SSG_CUDA(ctx, cudaMemsetAsync(sizeHist, 0, 3 * m1 * sizeof(unsigned), ctx->stream));
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_SMALLSEG, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_small_census");
+    k_small_census<<<gridFor(len + 1, 256), 256, (size_t)minSegSize * sizeof(unsigned), ctx->stream>>>(
+        segSize, len, (unsigned)minSegSize, off, sizeHist, counters);
     SSG_LAUNCHED(ctx);
-    size_t tmpBytes = 0;
+    size_t tmpBytes = 0, tmpBytes2 = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, off, off, (int)(len + 1), ctx->stream));
-    SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes));
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes2, sizeHist, bucketStart, (int)m1, ctx->stream));
+    SSG_TRY(ssg_reserve(ctx, ctx->cubTemp, tmpBytes > tmpBytes2 ? tmpBytes : tmpBytes2));
     SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, off, off, (int)(len + 1), ctx->stream));
     SSG_LAUNCHED(ctx);
+    SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes2, sizeHist, bucketStart, (int)m1, ctx->stream));
+    SSG_LAUNCHED(ctx);
+    SSG_TRY(ssg_fetch_counters(ctx));
+    const size_t numSmall = (size_t)ctx->hostCounters[C_NUM_SMALLSEG];
+    const size_t numSmallPix = (size_t)ctx->hostCounters[C_NUM_SMALLPIX];
+    if (numSmall == 0) return SSG_OK;   // nothing can be a candidate, now or later
 
+    // the arena holds the rewritten lists of merged segments; 2x the listed pixels covers the
+    // imagery seen so far several times over, and running out only costs speed (chained slices)
+    size_t arenaCap = 2 * numSmallPix;
+    if (const char *e = getenv("SSG_SMALL_ARENA_PCT")) arenaCap = numSmallPix * (size_t)atoi(e) / 100;
+    if (numSmallPix + arenaCap > 0xFFFFFFF0ull) arenaCap = 0xFFFFFFF0ull - numSmallPix;
     const size_t tbl = (size_t)len * sizeof(unsigned);
-    SSG_TRY(ssg_reserve(ctx, ctx->aux0, (size_t)N * sizeof(unsigned)));   // pixel array (<= N entries)
+    SSG_TRY(ssg_reserve(ctx, ctx->aux0, (numSmallPix + arenaCap) * sizeof(unsigned)));   // pixel store
+    SSG_TRY(ssg_reserve(ctx, ctx->aux1, 2 * tbl));                                       // slices
     SSG_TRY(ssg_reserve(ctx, ctx->nextChunk, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->tailChunk, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->mergeTo, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->pendHead, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->pendNext, tbl));
-    SSG_TRY(ssg_reserve(ctx, ctx->candList, tbl));
-    SSG_TRY(ssg_reserve(ctx, ctx->targetList, tbl));
+    // lists of the passes: grown log (u64), bucket, 2 target rings, 2 next rings (2x), 2 selections
+    SSG_TRY(ssg_reserve(ctx, ctx->candList, numSmall * 11 * sizeof(unsigned) + sizeof(SmallBarrier) +
+                                            SC_COUNT * sizeof(unsigned long long) + 64));
     unsigned *pix = bufp<unsigned>(ctx->aux0);
-    unsigned *fill = bufp<unsigned>(ctx->candList);   // free until the passes start
+    unsigned *sliceOff = bufp<unsigned>(ctx->aux1), *sliceLen = sliceOff + len;
+    unsigned *fill = bufp<unsigned>(ctx->pendNext);   // free until the passes start
     SSG_CUDA(ctx, cudaMemsetAsync(fill, 0, tbl, ctx->stream));
+    unsigned long long *grownLog = bufp<unsigned long long>(ctx->candList);
+    unsigned *bucketList = reinterpret_cast<unsigned *>(grownLog + numSmall);
+    unsigned *lists = bucketList + numSmall;
+    unsigned long long *ctr = reinterpret_cast<unsigned long long *>(
+        ((uintptr_t)(lists + 8 * numSmall) + 15) & ~(uintptr_t)15);
+    SmallBarrier *bar = reinterpret_cast<SmallBarrier *>(ctr + SC_COUNT);
+
+    SSG_PROF_BEGIN(ctx, "k_bucket_fill");
+    k_bucket_fill<<<gridFor(len, 256), 256, 2 * (size_t)minSegSize * sizeof(unsigned), ctx->stream>>>(
+        segSize, len, (unsigned)minSegSize, bucketStart, bucketFill, bucketList);
+    SSG_LAUNCHED(ctx);
     SSG_PROF_BEGIN(ctx, "k_list_fill");
     k_list_fill<<<gridFor(N, 256), 256, 0, ctx->stream>>>(seg, N, off, fill, pix);
     SSG_LAUNCHED(ctx);
     SSG_PROF_BEGIN(ctx, "k_list_sort");
-    k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(off, len, pix, bufp<unsigned>(ctx->nextChunk),
-                                                           bufp<unsigned>(ctx->tailChunk), bufp<unsigned>(ctx->mergeTo),
-                                                           bufp<unsigned>(ctx->pendHead));
+    k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(off, len, pix, sliceOff, sliceLen,
+                                                           bufp<unsigned>(ctx->nextChunk), bufp<unsigned>(ctx->tailChunk),
+                                                           bufp<unsigned>(ctx->mergeTo), bufp<unsigned>(ctx->pendHead));
     SSG_LAUNCHED(ctx);
 
     SmallState st;
     st.seg = seg; st.segSize = segSize; st.fsum = bufp<float>(ctx->fsum);
-    st.off = off; st.pix = pix;
+    st.off = off; st.pix = pix; st.sliceOff = sliceOff; st.sliceLen = sliceLen;
     st.nextChunk = bufp<unsigned>(ctx->nextChunk); st.tailChunk = bufp<unsigned>(ctx->tailChunk);
     st.mergeTo = bufp<unsigned>(ctx->mergeTo);
     st.pendHead = bufp<unsigned>(ctx->pendHead); st.pendNext = bufp<unsigned>(ctx->pendNext);
-    st.cand = bufp<unsigned>(ctx->candList); st.targets = bufp<unsigned>(ctx->targetList);
-    st.counters = counters;
+    st.bucketStart = bucketStart; st.bucketList = bucketList;
+    st.targets[0] = lists; st.targets[1] = lists + numSmall;
+    st.nextList[0] = lists + 2 * numSmall; st.nextList[1] = lists + 4 * numSmall;
+    st.selList[0] = lists + 6 * numSmall; st.selList[1] = lists + 7 * numSmall;
+    st.grownLog = grownLog;
+    st.ctr = ctr; st.bar = bar; st.cap = (unsigned)numSmall;
+    st.arenaBase = (unsigned)numSmallPix; st.arenaCap = (unsigned)arenaCap;
+    st.dbg = nullptr;
+    if (getenv("SSG_SMALL_DEBUG")) {   // phase timing of the persistent kernel, to stderr
+        SSG_TRY(ssg_reserve(ctx, ctx->targetList, 16 * sizeof(unsigned long long)));
+        st.dbg = bufp<unsigned long long>(ctx->targetList);
+    }
     st.nB = nB; st.nRows = nRows; st.nCols = nCols; st.four = four;
     st.len = (unsigned)len; st.minSegSize = minSegSize; st.thr = thr;
 
-    if (nB <= 4) SSG_TRY(run_small_passes<4>(ctx, st, numPasses));
-    else if (nB <= 8) SSG_TRY(run_small_passes<8>(ctx, st, numPasses));
-    else SSG_TRY(run_small_passes<SSG_MAX_BANDS>(ctx, st, numPasses));
-    *numElim = (int64_t)ctx->hostCounters[C_NUM_ELIM];
+    if (nB <= 4) SSG_TRY(run_small_passes<4>(ctx, st, numPasses, numElim));
+    else if (nB <= 8) SSG_TRY(run_small_passes<8>(ctx, st, numPasses, numElim));
+    else SSG_TRY(run_small_passes<SSG_MAX_BANDS>(ctx, st, numPasses, numElim));
     return SSG_OK;
 }
 

@@ -29,10 +29,22 @@ struct StitchTables {
 __global__ void __launch_bounds__(256)
 k_tile_max(const unsigned *__restrict__ tile, int64_t N, unsigned long long *counters)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned v = p < N ? tile[p] : 0u;
+    unsigned v = 0;
+    const int64_t base = (int64_t)blockIdx.x * blockDim.x * 8 + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int64_t p = base + (int64_t)i * blockDim.x;
+        if (p < N) v = max(v, tile[p]);
+    }
     v = __reduce_max_sync(0xffffffffu, v);
-    if (lane_id() == 0 && v) atomicMax(&counters[C_MAXLABEL], (unsigned long long)v);
+    __shared__ unsigned wmax[8];
+    if (lane_id() == 0) wmax[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) v = max(v, wmax[w]);
+        if (v) atomicMax(&counters[C_MAXLABEL], (unsigned long long)v);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -145,7 +157,8 @@ static int reserveTables(ssg_ctx *ctx, int64_t len, StitchTables &tb, unsigned *
 extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
                                       int64_t overlap, const uint32_t *topBDev, int64_t topBStride,
                                       const uint32_t *leftBDev, int64_t leftBStride, int64_t top,
-                                      int64_t bottom, int64_t left, int64_t right, ssg_tile_tables *out)
+                                      int64_t bottom, int64_t left, int64_t right, uint32_t maxIdHint,
+                                      ssg_tile_tables *out)
 {
     if (!ctx) return SSG_ERR_ARG;
     ctx->err.clear();
@@ -157,11 +170,14 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
 
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_MAXLABEL, 0, sizeof(unsigned long long), ctx->stream));
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    SSG_PROF_BEGIN(ctx, "k_tile_max");
-    k_tile_max<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, N, counters);
-    SSG_LAUNCHED(ctx);
-    SSG_TRY(ssg_fetch_counters(ctx));
-    const unsigned maxId = (unsigned)ctx->hostCounters[C_MAXLABEL];
+    unsigned maxId = maxIdHint;
+    if (maxId == 0) {       // the caller does not know the largest label: look for it
+        SSG_PROF_BEGIN(ctx, "k_tile_max");
+        k_tile_max<<<gridFor(N, 256 * 8), 256, 0, ctx->stream>>>(tileDev, N, counters);
+        SSG_LAUNCHED(ctx);
+        SSG_TRY(ssg_fetch_counters(ctx));
+        maxId = (unsigned)ctx->hostCounters[C_MAXLABEL];
+    }
     const int64_t len = (int64_t)maxId + 1;
 
     StitchTables tb;

@@ -540,7 +540,7 @@ class TiledSegmenter(object):
         tables = _lib.TileTables()
         with self.timings.interval('stitch_tables'):
             ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, ov, topB, topStride,
-                leftB, leftStride, top, bottom, left, right, ctypes.byref(tables))
+                leftB, leftStride, top, bottom, left, right, tile.numSegments, ctypes.byref(tables))
         n = int(tables.maxId) + 1
         rank = numpy.empty(n, dtype=numpy.uint32)
         flags = numpy.empty(n, dtype=numpy.uint8)

@@ -173,19 +173,22 @@ def test_big_values_inexact_sums(shepseg):
     _against_oracle(shepseg, img, 8, 200, None, True, None, 'bigvalues')
 
 
-def test_small_mode_host_loop_equals_persistent(shepseg):
-    """the cooperative persistent kernel and the host-driven launches are the same phases"""
+@pytest.mark.parametrize('env', [('SSG_SMALL_ARENA_PCT', '0'), ('SSG_SMALL_ARENA_PCT', '7'),
+    ('SSG_SMALL_BLOCKS_PER_SM', '1'), ('SSG_SMALL_BLOCKS_PER_SM', '4')],
+    ids=['no_arena_all_chained', 'arena_runs_out_midway', 'one_block_per_sm', 'four_blocks_per_sm'])
+def test_small_segment_list_storage_and_grid(shepseg, env):
+    """the merged pixel lists are rewritten into an arena while it lasts and chained after that;
+    neither that nor the size of the persistent grid may change a label"""
     img = synth.synth_v1(600, 700, 4, seed=10)
     km = goldenutil.Centres(synth.diagonal_centres(img, 40))
-    a = shepseg.doShepherdSegmentation(img, minSegmentSize=40, kmeansObj=km)
-    os.environ['SSG_SMALL_MODE'] = 'host'
+    want = oracle.doShepherdSegmentation(img, minSegmentSize=40, kmeansObj=km)
+    os.environ[env[0]] = env[1]
     try:
-        b = shepseg.doShepherdSegmentation(img, minSegmentSize=40, kmeansObj=km)
+        got = shepseg.doShepherdSegmentation(img, minSegmentSize=40, kmeansObj=km)
     finally:
-        del os.environ['SSG_SMALL_MODE']
-    same(a.segimg, b.segimg, 'host loop vs persistent')
-    assert a.smallSegmentsEliminated == b.smallSegmentsEliminated
-    assert a.timings['numSmallPasses'] == b.timings['numSmallPasses']
+        del os.environ[env[0]]
+    same(got.segimg, want.segimg, '%s=%s' % env)
+    assert got.smallSegmentsEliminated == want.smallSegmentsEliminated
 
 
 def test_edge_rasters(shepseg):
