@@ -113,57 +113,59 @@ def scene_centres(wl, img):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
-    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-        'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-
+    """SM clock, power and throttle reasons during the timed region (B200_PROFILING.md), read
+    through NVML in a thread of this process every 50 ms (an nvidia-smi child polling the driver
+    was seen to stall CUDA calls of the benchmark for tens of milliseconds)."""
     def __init__(self, device):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stopFlag = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
-                '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
-                stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        n = self.nvml
+        while not self.stopFlag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n,
+                    'nvmlDeviceGetCurrentClocksEventReasons') else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((sm, reasons, power))
+            except Exception:
+                pass
+            self.stopFlag.wait(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable']}
+        self.stopFlag.set()
+        self.thread.join(timeout=2)
+        n = self.nvml
         try:
-            self.proc.wait(timeout=5)
+            smMax = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm = []
-        smMax = None
+            smMax = None
+        names = (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40),
+            ('hw_power_brake_slowdown', 0x80), ('sw_power_cap', 0x4))
         reasons = set()
-        power = []
-        for line in self.lines:
-            f = [x.strip() for x in line.split(',')]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smMax = float(f[2])
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for (name, val) in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                    'sw_power_cap'), f[5:9]):
-                if val.lower().startswith('active'):
+        for (_, r, _) in self.samples:
+            for (name, bit) in names:
+                if r & bit:
                     reasons.add(name)
+        sm = [s[0] for s in self.samples]
+        power = [s[2] for s in self.samples]
         return {'sm_mhz': float(numpy.median(sm)) if sm else None, 'sm_max_mhz': smMax,
             'reasons': sorted(reasons), 'samples': len(sm),
             'power_w_max': max(power) if power else None}
@@ -333,8 +335,12 @@ def run_ours(args, wl):
         e0.record()
         last = None
         for _ in range(steps):
+            t0 = time.time()
             last = stepFn()
             exchange_ids(last[1])
+            if args.verbose_steps and rank == 0:
+                print('  step %s: %.1f ms' % (getattr(stepFn, '__name__', '?'), (time.time() - t0) * 1e3),
+                    file=sys.stderr, flush=True)
         torch.cuda.synchronize()
         e1.record()
         barrier()
@@ -456,6 +462,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--quick', action='store_true', help='2048-pixel raster and tiles (smoke runs only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--verbose-steps', action='store_true', help='print every timed step (stderr)')
     args = ap.parse_args()
     wl = dict(WORKLOAD)
     if args.quick:

@@ -60,6 +60,11 @@ const char *ssg_last_error(const ssg_ctx *ctx);
 /* the context's cudaStream_t, so a caller can order its own work / events against it */
 void *ssg_ctx_stream(ssg_ctx *ctx);
 int ssg_ctx_synchronize(ssg_ctx *ctx);
+/* size the context's device memory before the first tile arrives: the image staging and label
+ * buffers for tiles of up to maxPixels pixels of nBands bands of `dtype` (skipped when either is
+ * 0) and the per-call scratch slab (scratchBytes, or an estimate from maxPixels when 0).
+ * Optional: everything grows on demand, but growing means cudaMalloc / cudaFree mid-run. */
+int ssg_ctx_reserve(ssg_ctx *ctx, int64_t maxPixels, int nBands, int dtype, int64_t scratchBytes);
 /* pinned host memory for full-speed asynchronous copies */
 int ssg_host_alloc(size_t bytes, void **out);
 int ssg_host_free(void *p);

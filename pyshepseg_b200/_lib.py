@@ -66,6 +66,7 @@ SIGNATURES = {
     'ssg_last_error': (_c.c_char_p, [_vp]),
     'ssg_ctx_stream': (_vp, [_vp]),
     'ssg_ctx_synchronize': (_i, [_vp]),
+    'ssg_ctx_reserve': (_i, [_vp, _i64, _i, _i, _i64]),
     'ssg_host_alloc': (_i, [_sz, _c.POINTER(_vp)]),
     'ssg_host_free': (_i, [_vp]),
     'ssg_assign': (_i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _i, _i, _dbl, _vp]),

@@ -37,6 +37,15 @@ int ssg_ctx_create(int device, ssg_ctx **out)
         cudaFree(ctx->counters.p); cudaStreamDestroy(ctx->stream); delete ctx; return SSG_ERR_NOMEM;
     }
     for (auto &e : ctx->ev) cudaEventCreate(&e);
+    // everything that lives for one call only comes out of the slab; what outlives a call (the
+    // staged image, the resident labels, the stitch tables read by ssg_tile_tables_fetch, the
+    // centres, the counters) keeps an allocation of its own
+    DevBuf *scratch[] = {&ctx->cluster, &ctx->label, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->singles,
+                         &ctx->segSize, &ctx->isum, &ctx->fsum, &ctx->listOff, &ctx->nextChunk, &ctx->tailChunk,
+                         &ctx->mergeTo, &ctx->pendHead, &ctx->pendNext, &ctx->candList, &ctx->targetList, &ctx->lut,
+                         &ctx->flags, &ctx->blockCnt, &ctx->cubTemp, &ctx->sortKeys0, &ctx->sortKeys1, &ctx->sortVals0,
+                         &ctx->sortVals1, &ctx->emuStack, &ctx->stitch0, &ctx->stitch2, &ctx->stitch3};
+    for (DevBuf *b : scratch) { b->scratch = true; ctx->scratchBufs.push_back(b); }
     cudaStreamSynchronize(ctx->stream);
     *out = ctx;
     return SSG_OK;
@@ -47,13 +56,15 @@ void ssg_ctx_destroy(ssg_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->img, &ctx->cluster, &ctx->label, &ctx->seg, &ctx->aux0, &ctx->aux1, &ctx->aux2,
+    DevBuf *bufs[] = {&ctx->img, &ctx->cluster, &ctx->label, &ctx->seg, &ctx->aux0, &ctx->aux1, &ctx->aux2, &ctx->singles,
                       &ctx->segSize, &ctx->isum, &ctx->fsum, &ctx->listOff, &ctx->nextChunk, &ctx->tailChunk,
                       &ctx->mergeTo, &ctx->pendHead, &ctx->pendNext, &ctx->candList, &ctx->targetList, &ctx->lut,
                       &ctx->flags, &ctx->blockCnt, &ctx->cubTemp, &ctx->sortKeys0, &ctx->sortKeys1, &ctx->sortVals0,
                       &ctx->sortVals1, &ctx->emuStack, &ctx->centres, &ctx->counters, &ctx->stitch0, &ctx->stitch1,
                       &ctx->stitch2, &ctx->stitch3, &ctx->stitch4, &ctx->stitch5};
-    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : bufs) if (b->p && !b->scratch) cudaFree(b->p);
+    for (void *q : ctx->spills) cudaFree(q);
+    if (ctx->slab) cudaFree(ctx->slab);
     if (ctx->hostCounters) cudaFreeHost(ctx->hostCounters);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -126,6 +137,23 @@ int ssg_host_alloc(size_t bytes, void **out)
 int ssg_host_free(void *p)
 {
     if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return SSG_ERR_CUDA; }
+    return SSG_OK;
+}
+
+int ssg_ctx_reserve(ssg_ctx *ctx, int64_t maxPixels, int nBands, int dtype, int64_t scratchBytes)
+{
+    CTX_ENTER(ctx);
+    if (maxPixels < 0 || nBands < 0 || nBands > SSG_MAX_BANDS || scratchBytes < 0) SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument");
+    // measured on noisy 4-band imagery: about 40 bytes of scratch per pixel (cluster, root and
+    // single-pixel rasters, pixel lists, per-segment tables); a tile that needs more spills once
+    // and the slab follows
+    const size_t slab = scratchBytes > 0 ? (size_t)scratchBytes
+                                         : (size_t)maxPixels * (size_t)(40 + 2 * nBands) + ((size_t)64 << 20);
+    SSG_TRY(ssg_scratch_reset(ctx, slab));
+    if (nBands > 0 && maxPixels > 0) {
+        SSG_TRY(ssg_reserve(ctx, ctx->img, (size_t)maxPixels * nBands * dtypeSize(dtype)));
+        SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)maxPixels * sizeof(uint32_t)));
+    }
     return SSG_OK;
 }
 
@@ -213,6 +241,7 @@ int ssg_assign(ssg_ctx *ctx, const void *img, int dtype, int nBands, int64_t nRo
                const double *centres, int k, int hasNull, double nullVal, int32_t *out)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     SSG_TRY(check_image_args(ctx, img, dtype, nBands, nRows, nCols));
     if (!centres || (!out && nRows * nCols > 0)) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
     const int64_t N = nRows * nCols;
@@ -229,6 +258,7 @@ int ssg_clump(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int64_t nCols, in
               int fourConnected, uint32_t clumpId, uint32_t *out, uint32_t *nextId)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     if (nRows < 0 || nCols < 0 || nRows * nCols >= 0x7FFFFFF0ll) SSG_FAIL(ctx, SSG_ERR_ARG, "bad raster size");
     const int64_t N = nRows * nCols;
     if (nextId) *nextId = clumpId;
@@ -249,6 +279,7 @@ int ssg_clump(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int64_t nCols, in
 int ssg_make_seg_size(ssg_ctx *ctx, const uint32_t *seg, int64_t nPixels, uint32_t *segSize, int64_t len)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     if (nPixels < 0 || len < 0 || (!seg && nPixels > 0) || (!segSize && len > 0)) SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument");
     if (len == 0) return SSG_OK;
     SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)(nPixels ? nPixels : 1) * sizeof(uint32_t)));
@@ -265,6 +296,7 @@ int ssg_eliminate_single_pixels(ssg_ctx *ctx, const void *img, int dtype, int nB
                                 uint32_t minSegId, int fourConnected, int64_t *numMoved)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     SSG_TRY(check_image_args(ctx, img, dtype, nBands, nRows, nCols));
     const int64_t N = nRows * nCols;
     if (numMoved) *numMoved = 0;
@@ -294,6 +326,7 @@ int ssg_eliminate_small_segments(ssg_ctx *ctx, uint32_t *seg, const void *img, i
                                  int64_t *numEliminated)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     SSG_TRY(check_image_args(ctx, img, dtype, nBands, nRows, nCols));
     const int64_t N = nRows * nCols;
     if (numEliminated) *numEliminated = 0;
@@ -343,8 +376,9 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     SSG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     uint32_t numClumps = 0, numOver = 0;
+    int64_t numSingles = -1;
     SSG_TRY(ssgk_clump(ctx, bufp<int32_t>(ctx->cluster), prm->nRows, prm->nCols, 0, prm->fourConnected, 1,
-                       segDev, &numClumps, &numOver));
+                       segDev, &numClumps, &numOver, &numSingles));
     SSG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     const int64_t len = (int64_t)numClumps + 1;
     unsigned *segSize = bufp<unsigned>(ctx->segSize);
@@ -352,7 +386,8 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     int64_t moved = 0;
     uint32_t rounds = 0;
     SSG_TRY(ssgk_eliminate_single(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev,
-                                  segSize, len, prm->fourConnected, &moved, &rounds));
+                                  segSize, len, prm->fourConnected, &moved, &rounds,
+                                  numSingles >= 0 ? bufp<unsigned>(ctx->singles) : nullptr, numSingles));
     // ids that lost their only pixel = what the reference reports as singlePixelsEliminated
     // (oldMaxSegId - seg.max() after its order-preserving relabel, shepseg.py:226-227)
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, sizeof(unsigned long long), ctx->stream));
@@ -402,6 +437,7 @@ int ssg_segment_tile_device(ssg_ctx *ctx, const void *imgDev, const ssg_tile_par
                             uint32_t *segOutDev, ssg_tile_result *res)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     SSG_TRY(check_tile_params(ctx, imgDev, prm, res));
     const int64_t N = prm->nRows * prm->nCols;
     uint32_t *segDev = segOutDev;
@@ -420,6 +456,7 @@ int ssg_segment_tile(ssg_ctx *ctx, const void *imgHost, const ssg_tile_params *p
                      uint32_t *segOutHost, ssg_tile_result *res)
 {
     CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
     SSG_TRY(check_tile_params(ctx, imgHost, prm, res));
     const int64_t N = prm->nRows * prm->nCols;
     SSG_TRY(upload_image(ctx, imgHost, prm->dtype, prm->nBands, N));

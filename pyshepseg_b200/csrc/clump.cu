@@ -269,24 +269,63 @@ k_number_roots(const unsigned *__restrict__ label, int64_t N, const unsigned *__
         if (isRoot[i]) seg[base + i] = id++;
 }
 
+// ids of the roots to every pixel + the size table.  A root whose later neighbours (right and
+// below; a root is the raster-first pixel of its clump) do not point at it is a clump of one
+// pixel: those are listed for the single-pixel stage, which then needs no scan of its own.
+#define GATHER_PIX 1024   // pixels per block (4 strips of 256)
 __global__ void __launch_bounds__(256)
-k_gather_ids(const unsigned *__restrict__ label, int64_t N, unsigned *seg, unsigned *segSize)
+k_gather_ids(const unsigned *__restrict__ label, int64_t nRows, int64_t nCols, int four,
+             unsigned *seg, unsigned *segSize, unsigned *singles, unsigned long long *counters)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned id = 0;
-    bool valid = p < N;
-    if (valid) {
-        unsigned l = label[p];
-        if (l == SSG_NIL) id = 0;
-        else if (l == (unsigned)p) id = seg[p];
-        else id = __ldcg(seg + l);   // written by k_number_roots (previous launch)
-        if (l != (unsigned)p) seg[p] = id;
+    __shared__ unsigned sList[GATHER_PIX];
+    __shared__ unsigned sCount;
+    __shared__ unsigned long long sBase;
+    const int64_t N = nRows * nCols;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < GATHER_PIX / 256; it++) {
+        const int64_t p = (int64_t)blockIdx.x * GATHER_PIX + it * 256 + threadIdx.x;
+        unsigned id = 0;
+        const bool valid = p < N;
+        bool single = false;
+        if (valid) {
+            const unsigned l = label[p];
+            if (l == SSG_NIL) id = 0;
+            else if (l == (unsigned)p) id = seg[p];
+            else id = __ldcg(seg + l);   // written by k_number_roots (previous launch)
+            if (l != (unsigned)p) seg[p] = id;
+            else if (singles) {
+                const int64_t y = p / nCols, x = p % nCols;
+                const bool hasR = x + 1 < nCols, hasD = y + 1 < nRows;
+                bool grown = (hasR && label[p + 1] == l) || (hasD && label[p + nCols] == l);
+                if (!four && hasD)
+                    grown = grown || (x > 0 && label[p + nCols - 1] == l) || (hasR && label[p + nCols + 1] == l);
+                single = !grown;
+            }
+        }
+        if (singles) {     // block-local list first: one global atomic per block
+            const unsigned m = __ballot_sync(0xffffffffu, single);
+            unsigned base = 0;
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                if ((int)lane_id() == leader) base = atomicAdd(&sCount, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (single) sList[base + __popc(m & ((1u << lane_id()) - 1u))] = (unsigned)p;
+            }
+        }
+        // size histogram: one atomic per distinct id per warp
+        const unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, id);
+            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&segSize[id], (unsigned)__popc(peers));
+        }
     }
-    // size histogram: one atomic per distinct id per warp
-    unsigned active = __ballot_sync(0xffffffffu, valid);
-    if (!valid) return;
-    unsigned peers = __match_any_sync(active, id);
-    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&segSize[id], (unsigned)__popc(peers));
+    if (!singles) return;
+    __syncthreads();
+    if (threadIdx.x == 0 && sCount) sBase = atomicAdd(&counters[C_NUM_SINGLEPIX], (unsigned long long)sCount);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < sCount; i += 256) singles[sBase + i] = sList[i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -296,6 +335,7 @@ k_count_oversized(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
     const int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool over = s < len && segSize[s] > SSG_MAX_CLUMP_SIZE + 1;
     bool single = s < len && segSize[s] == 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[C_NULL_SINGLE] = segSize[0] == 1 ? 1ull : 0ull;
     unsigned mo = __ballot_sync(0xffffffffu, over);
     unsigned ms = __ballot_sync(0xffffffffu, single);
     if (lane_id() == 0) {
@@ -305,9 +345,11 @@ k_count_oversized(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
 }
 
 // labels (root pointers) -> dense ids in seg + size table; returns the number of roots
-static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t N, unsigned clumpId,
-                              unsigned *seg, unsigned *numRoots)
+static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t nRows, int64_t nCols,
+                              int four, unsigned clumpId, unsigned *seg, unsigned *numRoots,
+                              bool listSingles)
 {
+    const int64_t N = nRows * nCols;
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
     const int64_t nBlocks = (N + NUM_BLOCK_PIX - 1) / NUM_BLOCK_PIX;
     SSG_TRY(ssg_reserve(ctx, ctx->blockCnt, (size_t)nBlocks * 2 * sizeof(unsigned)));
@@ -331,8 +373,15 @@ static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t N, un
     const size_t len = (size_t)clumpId + *numRoots;
     SSG_TRY(ssg_reserve(ctx, ctx->segSize, len * sizeof(unsigned)));
     SSG_CUDA(ctx, cudaMemsetAsync(ctx->segSize.p, 0, len * sizeof(unsigned), ctx->stream));
+    unsigned *singles = nullptr;
+    if (listSingles) {
+        SSG_TRY(ssg_reserve(ctx, ctx->singles, (size_t)N * sizeof(unsigned)));
+        singles = bufp<unsigned>(ctx->singles);
+        SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_SINGLEPIX, 0, sizeof(unsigned long long), ctx->stream));
+    }
     SSG_PROF_BEGIN(ctx, "k_gather_ids");
-    k_gather_ids<<<gridFor(N, 256), 256, 0, ctx->stream>>>(label, N, seg, bufp<unsigned>(ctx->segSize));
+    k_gather_ids<<<gridFor(N, GATHER_PIX), 256, 0, ctx->stream>>>(label, nRows, nCols, four, seg, bufp<unsigned>(ctx->segSize),
+                                                          singles, counters);
     SSG_LAUNCHED(ctx);
     return SSG_OK;
 }
@@ -440,7 +489,7 @@ static int split_oversized(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int6
 // ---- driver ----------------------------------------------------------------------------------
 int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t nCols,
                int32_t ignoreVal, int four, uint32_t clumpId, uint32_t *segDev,
-               uint32_t *numClumps, uint32_t *numOversized)
+               uint32_t *numClumps, uint32_t *numOversized, int64_t *singlesOut)
 {
     const int64_t N = nRows * nCols;
     *numClumps = 0;
@@ -466,7 +515,7 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
         SSG_LAUNCHED(ctx);
     }
     unsigned numRoots = 0;
-    SSG_TRY(number_from_labels(ctx, label, N, clumpId, segDev, &numRoots));
+    SSG_TRY(number_from_labels(ctx, label, nRows, nCols, four, clumpId, segDev, &numRoots, singlesOut != nullptr));
     // oversized regions / single-pixel clumps
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_OVERSIZED, 0, 2 * sizeof(unsigned long long), ctx->stream));
     SSG_PROF_BEGIN(ctx, "k_count_oversized");
@@ -478,7 +527,7 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
     *numOversized = nOver;
     if (nOver > 0) {
         SSG_TRY(split_oversized(ctx, clusterDev, nRows, nCols, four, label, segDev, (int64_t)clumpId + numRoots));
-        SSG_TRY(number_from_labels(ctx, label, N, clumpId, segDev, &numRoots));
+        SSG_TRY(number_from_labels(ctx, label, nRows, nCols, four, clumpId, segDev, &numRoots, singlesOut != nullptr));
         SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_OVERSIZED, 0, 2 * sizeof(unsigned long long), ctx->stream));
         SSG_PROF_BEGIN(ctx, "k_count_oversized");
         k_count_oversized<<<gridFor(numRoots, 256), 256, 0, ctx->stream>>>(bufp<unsigned>(ctx->segSize), (int64_t)clumpId,
@@ -487,6 +536,13 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
         SSG_TRY(ssg_fetch_counters(ctx));
     }
     *numClumps = numRoots;
+    if (singlesOut) {
+        // the list stands for "every pixel whose segment has one pixel" unless the null segment
+        // is such a pixel too (shepseg.py:652 treats it like any other segment)
+        const int64_t listed = (int64_t)ctx->hostCounters[C_NUM_SINGLEPIX];
+        const bool ok = ctx->hostCounters[C_NULL_SINGLE] == 0 && listed == (int64_t)ctx->hostCounters[C_NUM_SINGLES];
+        *singlesOut = ok ? listed : -1;
+    }
     return SSG_OK;
 }
 

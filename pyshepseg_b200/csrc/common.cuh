@@ -17,6 +17,7 @@
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool scratch = false;   // carved out of the context's slab, valid for one entry-point call
 };
 
 // One context per worker thread: a stream, named scratch buffers that only ever grow,
@@ -34,6 +35,7 @@ struct ssg_ctx {
     DevBuf label;     // uint32 root pixel per pixel (clump); later scratch
     DevBuf seg;       // uint32 segment ids
     DevBuf aux0, aux1, aux2;   // N-sized scratch (lists, moves)
+    DevBuf singles;   // pixels of the single-pixel clumps, listed while the clumps are numbered
     // per-segment tables
     DevBuf segSize, isum, fsum, listOff, nextChunk, tailChunk, mergeTo, pendHead, pendNext,
            candList, targetList, lut, flags;
@@ -45,6 +47,16 @@ struct ssg_ctx {
     std::vector<double> centresStage;
     DevBuf counters;  // small device counter block (see enum Counter)
     DevBuf stitch0, stitch1, stitch2, stitch3, stitch4, stitch5;
+
+    // Scratch of one call comes out of one slab by bumping a pointer (cudaMalloc / cudaFree
+    // synchronise the whole device, and the worker contexts of a tiled run would otherwise each
+    // grow three dozen buffers the first time they meet the largest tile).  A call that needs
+    // more than the slab holds gets plain allocations for the excess; the slab is regrown to the
+    // observed need at the start of the next call.
+    char *slab = nullptr;
+    size_t slabCap = 0, slabUsed = 0, slabNeed = 0, spillBytes = 0;
+    std::vector<void *> spills;
+    std::vector<DevBuf *> scratchBufs;
 
     uint64_t *hostCounters = nullptr;   // pinned mirror of `counters`
     cudaEvent_t ev[8] = {};
@@ -71,6 +83,8 @@ enum Counter {
     C_NUM_ROOTS = 0,
     C_NUM_OVERSIZED,
     C_NUM_SINGLES,
+    C_NUM_SINGLEPIX,   // single-pixel clumps listed by the numbering pass
+    C_NULL_SINGLE,     // exactly one null pixel (it counts as a single-pixel segment)
     C_NUM_MOVES,
     C_NUM_LEFT,
     C_NUM_ALIVE,
@@ -149,10 +163,31 @@ static inline void ssg_prof_end(ssg_ctx *ctx)
         SSG_CUDA(ctx, cudaGetLastError());                              \
     } while (0)
 
-// grow-only device buffer
+// device buffer of at least `bytes`: scratch buffers come out of the slab (contents are lost
+// when they grow), the few persistent ones are grow-only allocations of their own
 static inline int ssg_reserve(ssg_ctx *ctx, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return SSG_OK;
+    if (b.scratch) {
+        const size_t want = (bytes + 255) & ~(size_t)255;
+        if (ctx->slabUsed + want <= ctx->slabCap) {
+            b.p = ctx->slab + ctx->slabUsed;
+            ctx->slabUsed += want;
+        } else {
+            void *q = nullptr;
+            cudaError_t e = cudaMalloc(&q, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                SSG_FAIL(ctx, SSG_ERR_NOMEM, "cudaMalloc of %zu scratch bytes failed: %s", want, cudaGetErrorString(e));
+            }
+            ctx->spills.push_back(q);
+            ctx->spillBytes += want;
+            b.p = q;
+        }
+        b.cap = want;
+        if (ctx->slabUsed + ctx->spillBytes > ctx->slabNeed) ctx->slabNeed = ctx->slabUsed + ctx->spillBytes;
+        return SSG_OK;
+    }
     if (b.p) {
         SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         SSG_CUDA(ctx, cudaFree(b.p));
@@ -173,6 +208,36 @@ static inline int ssg_reserve(ssg_ctx *ctx, DevBuf &b, size_t bytes)
                  cudaGetErrorString(e));
     }
     b.cap = want;
+    return SSG_OK;
+}
+
+// start of an entry-point call: every scratch buffer is forgotten, spilled allocations of the
+// previous call are returned and the slab is regrown if that call needed more than it holds
+static inline int ssg_scratch_reset(ssg_ctx *ctx, size_t atLeast = 0)
+{
+    for (DevBuf *b : ctx->scratchBufs) { b->p = nullptr; b->cap = 0; }
+    ctx->slabUsed = 0;
+    size_t need = ctx->slabNeed > atLeast ? ctx->slabNeed : atLeast;
+    if (!ctx->spills.empty() || need > ctx->slabCap) {
+        SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (void *q : ctx->spills) cudaFree(q);
+        ctx->spills.clear();
+        ctx->spillBytes = 0;
+    }
+    if (need > ctx->slabCap) {
+        if (ctx->slab) cudaFree(ctx->slab);
+        ctx->slab = nullptr;
+        ctx->slabCap = 0;
+        size_t want = need + need / 8 + (1u << 20);
+        void *q = nullptr;
+        if (cudaMalloc(&q, want) != cudaSuccess) {
+            cudaGetLastError();
+            want = need;
+            if (cudaMalloc(&q, want) != cudaSuccess) { cudaGetLastError(); q = nullptr; want = 0; }
+        }
+        ctx->slab = (char *)q;      // without a slab every reservation spills: slow, still correct
+        ctx->slabCap = want;
+    }
     return SSG_OK;
 }
 
@@ -224,13 +289,18 @@ int ssgk_group_pixels(ssg_ctx *ctx, const unsigned *segDev, int64_t N, const uns
 // stage entry points implemented in the other translation units ------------------------
 int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t N,
                 const double *centresHost, int k, int hasNull, double nullVal, int32_t *outDev);
+// singlesOut (optional): receives the number of single-pixel clumps whose pixels were listed in
+// ctx->singles, or -1 if the list cannot stand in for a scan (a lone null pixel exists)
 int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t nCols,
                int32_t ignoreVal, int four, uint32_t clumpId, uint32_t *segDev,
-               uint32_t *numClumps, uint32_t *numOversized);
+               uint32_t *numClumps, uint32_t *numOversized, int64_t *singlesOut = nullptr);
 int ssgk_seg_size(ssg_ctx *ctx, const uint32_t *segDev, int64_t N, uint32_t *sizeDev, int64_t len);
+// cand0 / nCand0: the pixels of all single-pixel segments if the caller has them (device list),
+// else nullptr / -1 and the first round scans the raster
 int ssgk_eliminate_single(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
                           int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, int64_t len,
-                          int four, int64_t *numMoved, uint32_t *numRounds);
+                          int four, int64_t *numMoved, uint32_t *numRounds,
+                          const unsigned *cand0 = nullptr, int64_t nCand0 = -1);
 int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, uint32_t maxSegId,
                          int minSegSize, double thr, int four, int64_t *numElim,

@@ -34,52 +34,66 @@ namespace cg = cooperative_groups;
 // ====================================================================================
 // single pixels
 // ====================================================================================
-template <typename T>
-__device__ __forceinline__ long long pixel_dist(const T *__restrict__ img, int nB, int64_t N,
-                                                int64_t p, int64_t q)
-{
-    unsigned long long d = 0;   // wraps like the reference's int64
-    for (int b = 0; b < nB; b++) {
-        long long df = (long long)img[(size_t)b * N + p] - (long long)img[(size_t)b * N + q];
-        d += (unsigned long long)(df * df);
-    }
-    return (long long)d;
-}
-
 // findNearestNeighbourPixel (shepseg.py:677-736): rows outer, columns inner, first strict
-// minimum, only neighbours whose segment has more than one pixel.
-template <typename T>
+// minimum of the int64 squared distance, only neighbours whose segment has more than one pixel.
+// The loads go out level by level (labels, sizes, then one band of all neighbours at a time) so
+// that their latencies overlap.
+template <typename T, bool FOUR>
 __device__ bool nearest_neighbour(const T *__restrict__ img, int nB, int64_t nRows, int64_t nCols,
                                   const unsigned *__restrict__ seg,
-                                  const unsigned *__restrict__ segSize, int four, int64_t p,
+                                  const unsigned *__restrict__ segSize, int64_t p,
                                   unsigned *newSeg)
 {
     const int64_t N = nRows * nCols;
     const int64_t i = p / nCols, j = p % nCols;
-    long long minD = -1;
-    unsigned best = 0;
-    bool found = false;
-    for (int64_t ii = (i > 0 ? i - 1 : 0); ii <= (i + 1 < nRows ? i + 1 : nRows - 1); ii++) {
-        for (int64_t jj = (j > 0 ? j - 1 : 0); jj <= (j + 1 < nCols ? j + 1 : nCols - 1); jj++) {
-            if (four && ii != i && jj != j) continue;
-            const int64_t q = ii * nCols + jj;
-            const unsigned sn = seg[q];
-            if (segSize[sn] > 1) {
-                long long d = pixel_dist(img, nB, N, p, q);
-                if (minD < 0 || d < minD) { minD = d; best = sn; found = true; }
-            }
+    unsigned sn[8], sz[8];
+    int64_t qi[8];
+    bool ok[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int w = q < 4 ? q : q + 1;            // window cell, centre skipped
+        const int dy = w / 3 - 1, dx = w % 3 - 1;
+        const int64_t ii = i + dy, jj = j + dx;
+        ok[q] = ii >= 0 && ii < nRows && jj >= 0 && jj < nCols && !(FOUR && dy != 0 && dx != 0);
+        qi[q] = ok[q] ? ii * nCols + jj : p;
+        sn[q] = ok[q] ? seg[qi[q]] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) sz[q] = ok[q] ? segSize[sn[q]] : 0u;
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { ok[q] = ok[q] && sz[q] > 1; any |= ok[q]; }
+    *newSeg = 0;
+    if (!any) return false;
+    unsigned long long d[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // wraps like the reference's int64
+    for (int b = 0; b < nB; b++) {
+        const T *plane = img + (size_t)b * N;
+        const int own = (int)plane[p];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (!ok[q]) continue;
+            const int df = own - (int)plane[qi[q]];
+            d[q] += (unsigned long long)((long long)df * (long long)df);
         }
     }
+    long long minD = -1;
+    unsigned best = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (!ok[q]) continue;
+        const long long dq = (long long)d[q];
+        if (minD < 0 || dq < minD) { minD = dq; best = sn[q]; }
+    }
     *newSeg = best;
-    return found;
+    return true;
 }
 
 // decide phase of mergeSinglePixels (shepseg.py:649-660).  candIn == nullptr: scan every
 // pixel (first round); otherwise scan the pixels left over from the previous round.
-template <typename T>
+template <typename T, bool FOUR>
 __global__ void __launch_bounds__(256)
 k_single_decide(const T *__restrict__ img, int nB, int64_t nRows, int64_t nCols,
-                const unsigned *__restrict__ seg, const unsigned *__restrict__ segSize, int four,
+                const unsigned *__restrict__ seg, const unsigned *__restrict__ segSize,
                 const unsigned *__restrict__ candIn, int64_t nIn, unsigned *movePix,
                 unsigned *moveSeg, unsigned *candOut, unsigned long long *counters)
 {
@@ -92,7 +106,7 @@ k_single_decide(const T *__restrict__ img, int nB, int64_t nRows, int64_t nCols,
     }
     unsigned newSeg = 0;
     bool found = false;
-    if (cand) found = nearest_neighbour(img, nB, nRows, nCols, seg, segSize, four, p, &newSeg);
+    if (cand) found = nearest_neighbour<T, FOUR>(img, nB, nRows, nCols, seg, segSize, p, &newSeg);
     unsigned long long s0 = warp_claim(&counters[C_NUM_MOVES], cand && found);
     if (cand && found) { movePix[s0] = (unsigned)p; moveSeg[s0] = newSeg; }
     unsigned long long s1 = warp_claim(&counters[C_NUM_LEFT], cand && !found);
@@ -126,7 +140,8 @@ k_count_size_eq(const unsigned *__restrict__ segSize, int64_t lo, int64_t len, u
 template <typename T>
 static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, int64_t nCols,
                               unsigned *seg, unsigned *segSize, int64_t len, int four,
-                              int64_t *numMoved, unsigned *numRounds)
+                              int64_t *numMoved, unsigned *numRounds, const unsigned *cand0,
+                              int64_t nCand0)
 {
     const int64_t N = nRows * nCols;
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
@@ -134,12 +149,16 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
     *numRounds = 0;
     if (N == 0) return SSG_OK;
     // how many single-pixel segments are there (the lone null pixel counts, shepseg.py:652)
-    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_SINGLES, 0, sizeof(unsigned long long), ctx->stream));
-    SSG_PROF_BEGIN(ctx, "k_count_size_eq");
-    k_count_size_eq<<<gridFor(len, 256), 256, 0, ctx->stream>>>(segSize, 0, len, 1u, counters + C_NUM_SINGLES);
-    SSG_LAUNCHED(ctx);
-    SSG_TRY(ssg_fetch_counters(ctx));
-    const int64_t nSingles = (int64_t)ctx->hostCounters[C_NUM_SINGLES];
+    int64_t nSingles = nCand0;
+    if (cand0 == nullptr || nCand0 < 0) {
+        cand0 = nullptr;
+        SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_SINGLES, 0, sizeof(unsigned long long), ctx->stream));
+        SSG_PROF_BEGIN(ctx, "k_count_size_eq");
+        k_count_size_eq<<<gridFor(len, 256), 256, 0, ctx->stream>>>(segSize, 0, len, 1u, counters + C_NUM_SINGLES);
+        SSG_LAUNCHED(ctx);
+        SSG_TRY(ssg_fetch_counters(ctx));
+        nSingles = (int64_t)ctx->hostCounters[C_NUM_SINGLES];
+    }
     if (nSingles == 0) return SSG_OK;
     const size_t cap = (size_t)nSingles * sizeof(unsigned);
     SSG_TRY(ssg_reserve(ctx, ctx->aux0, cap));
@@ -148,14 +167,18 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
     unsigned *movePix = bufp<unsigned>(ctx->aux0), *moveSeg = bufp<unsigned>(ctx->aux1);
     unsigned *candA = bufp<unsigned>(ctx->aux2), *candB = candA + nSingles;
 
-    const unsigned *candIn = nullptr;
-    int64_t nIn = N;
+    const unsigned *candIn = cand0;
+    int64_t nIn = cand0 ? nSingles : N;
     unsigned *candOut = candA;
     while (true) {
         SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_MOVES, 0, 2 * sizeof(unsigned long long), ctx->stream));
         SSG_PROF_BEGIN(ctx, "k_single_decide");
-        k_single_decide<T><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize, four,
-                                                                       candIn, nIn, movePix, moveSeg, candOut, counters);
+        if (four)
+            k_single_decide<T, true><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize,
+                                                                                 candIn, nIn, movePix, moveSeg, candOut, counters);
+        else
+            k_single_decide<T, false><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize,
+                                                                                  candIn, nIn, movePix, moveSeg, candOut, counters);
         SSG_LAUNCHED(ctx);
         SSG_TRY(ssg_fetch_counters(ctx));
         const int64_t nMoves = (int64_t)ctx->hostCounters[C_NUM_MOVES];
@@ -176,12 +199,13 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
 
 int ssgk_eliminate_single(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
                           int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, int64_t len,
-                          int four, int64_t *numMoved, uint32_t *numRounds)
+                          int four, int64_t *numMoved, uint32_t *numRounds, const unsigned *cand0,
+                          int64_t nCand0)
 {
     switch (dtype) {
-    case SSG_U8: return eliminate_single_t<uint8_t>(ctx, (const uint8_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds);
-    case SSG_U16: return eliminate_single_t<uint16_t>(ctx, (const uint16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds);
-    case SSG_I16: return eliminate_single_t<int16_t>(ctx, (const int16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds);
+    case SSG_U8: return eliminate_single_t<uint8_t>(ctx, (const uint8_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0);
+    case SSG_U16: return eliminate_single_t<uint16_t>(ctx, (const uint16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0);
+    case SSG_I16: return eliminate_single_t<int16_t>(ctx, (const int16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0);
     default: SSG_FAIL(ctx, SSG_ERR_ARG, "unsupported dtype code %d", dtype);
     }
 }
@@ -600,45 +624,63 @@ __device__ void phase_find(const SmallState &st, unsigned t, const CandSource &s
             for (int b = 0; b < NBMAX; b++)
                 if (b < nB) ms[b] = seg_mean(st.fsum[(size_t)s * nB + b], t);
             unsigned posBase = 0;
-            unsigned lastU = 0;
-            float lastD = 0.0f;
             for (unsigned ch = s; ch != SSG_NIL; ch = st.nextChunk[ch]) {
                 const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
                 for (unsigned i = sub; i < n; i += G) {
                     const unsigned p = st.pix[o + i];
                     const unsigned k = posBase + i;
                     const int64_t y = p / st.nCols, x = p % st.nCols;
+                    // The loads of one pixel's neighbourhood are issued level by level (labels,
+                    // then sizes, then sums) so that their latencies overlap: the phase is a
+                    // chain of dependent gathers and nothing else.
+                    unsigned nu[8], su[8];
+                    bool ok[8];
 #pragma unroll
-                    for (int dy = -1; dy <= 1; dy++) {
-                        const int64_t yy = y + dy;
-                        if (yy < 0 || yy >= st.nRows) continue;
+                    for (int q = 0; q < 8; q++) {
+                        const int w = q < 4 ? q : q + 1;            // window cell, centre skipped
+                        const int dy = w / 3 - 1, dx = w % 3 - 1;   // rows outer, columns inner
+                        const int64_t yy = y + dy, xx = x + dx;
+                        ok[q] = yy >= 0 && yy < st.nRows && xx >= 0 && xx < st.nCols &&
+                                !(st.four && dy != 0 && dx != 0);
+                        nu[q] = ok[q] ? st.seg[yy * st.nCols + xx] : 0u;
+                    }
 #pragma unroll
-                        for (int dx = -1; dx <= 1; dx++) {
-                            const int64_t xx = x + dx;
-                            if (xx < 0 || xx >= st.nCols) continue;
-                            if (st.four && dy != 0 && dx != 0) continue;
-                            const unsigned u = st.seg[yy * st.nCols + xx];
-                            if (u == s || u == 0) continue;
-                            const unsigned su = st.segSize[u];
-                            if (su <= t) continue;
-                            float d;
-                            if (u == lastU) d = lastD;
-                            else {
-                                d = 0.0f;
+                    for (int q = 0; q < 8; q++) {
+                        ok[q] = ok[q] && nu[q] != s && nu[q] != 0;
 #pragma unroll
-                                for (int b = 0; b < NBMAX; b++) {
-                                    if (b < nB) {
-                                        float mu = seg_mean(st.fsum[(size_t)u * nB + b], su);
-                                        float df = __fsub_rn(ms[b], mu);
-                                        d = __fadd_rn(d, __fmul_rn(df, df));
-                                    }
+                        for (int r = 0; r < q; r++)      // a repeat can never win: same distance, later
+                            if (nu[r] == nu[q]) ok[q] = false;
+                        su[q] = ok[q] ? st.segSize[nu[q]] : 0u;
+                    }
+                    constexpr int BATCH = NBMAX <= 4 ? 4 : 2;
+#pragma unroll
+                    for (int q0 = 0; q0 < 8; q0 += BATCH) {
+                        float fs[BATCH][NBMAX];
+#pragma unroll
+                        for (int e = 0; e < BATCH; e++) {
+                            ok[q0 + e] = ok[q0 + e] && su[q0 + e] > t;     // strictly larger, shepseg.py:1052
+#pragma unroll
+                            for (int b = 0; b < NBMAX; b++)
+                                fs[e][b] = (ok[q0 + e] && b < nB) ? st.fsum[(size_t)nu[q0 + e] * nB + b] : 0.0f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < BATCH; e++) {
+                            if (!ok[q0 + e]) continue;
+                            float d = 0.0f;
+#pragma unroll
+                            for (int b = 0; b < NBMAX; b++) {
+                                if (b < nB) {
+                                    const float mu = seg_mean(fs[e][b], su[q0 + e]);
+                                    const float df = __fsub_rn(ms[b], mu);
+                                    d = __fadd_rn(d, __fmul_rn(df, df));
                                 }
-                                lastU = u; lastD = d;
                             }
+                            const int q = q0 + e;
+                            const unsigned cell = (unsigned)(q < 4 ? q : q + 1);
                             const unsigned long long key =
                                 ((unsigned long long)__float_as_uint(d) << 32) |
-                                (unsigned long long)(k * 16u + (unsigned)((dy + 1) * 3 + (dx + 1)));
-                            if (key < bestKey) { bestKey = key; bestU = u; }
+                                (unsigned long long)(k * 16u + cell);
+                            if (key < bestKey) { bestKey = key; bestU = nu[q]; }
                         }
                     }
                 }
@@ -814,7 +856,7 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
 // merged nothing; the candidates of pass p+1 are exactly the unmerged candidates of pass p
 // (merging only creates sizes larger than the current one).
 template <int NBMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_small_persistent(SmallState st)
 {
     __shared__ unsigned long long cur[SF_COUNT];
@@ -886,13 +928,14 @@ template <int NBMAX>
 static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses, int64_t *numElim)
 {
     SSG_CUDA(ctx, cudaMemsetAsync(st.ctr, 0, SC_COUNT * sizeof(unsigned long long) + sizeof(SmallBarrier), ctx->stream));
-    int perSM = 0;
-    SSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_small_persistent<NBMAX>, 256, 0));
+    int perSM = 0, threads = 512;
+    if (const char *e = getenv("SSG_SMALL_THREADS")) threads = atoi(e) == 256 ? 256 : (atoi(e) == 128 ? 128 : 512);
+    SSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_small_persistent<NBMAX>, threads, 0));
     if (perSM < 1) SSG_FAIL(ctx, SSG_ERR_CUDA, "persistent merge kernel does not fit on an SM");
-    int want = 2;
+    int want = 1;   // fewer, fatter blocks: the grid barrier is what a pass pays most for
     if (const char *e = getenv("SSG_SMALL_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
     if (perSM > want) perSM = want;
-    dim3 grid((unsigned)(ctx->numSMs * perSM)), block(256);
+    dim3 grid((unsigned)(ctx->numSMs * perSM)), block((unsigned)threads);
     void *args[] = {&st};
     SSG_PROF_BEGIN(ctx, "k_small_persistent");
     SSG_CUDA(ctx, cudaLaunchCooperativeKernel((void *)k_small_persistent<NBMAX>, grid, block, args, 0, ctx->stream));

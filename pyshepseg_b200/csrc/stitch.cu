@@ -164,6 +164,7 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     ctx->err.clear();
     SSG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!tileDev || !out || ysize <= 0 || xsize <= 0 || overlap < 0) SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument");
+    SSG_TRY(ssg_scratch_reset(ctx));
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
     const int64_t N = ysize * xsize;
     memset(out, 0, sizeof(*out));
@@ -309,6 +310,7 @@ extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64
     SSG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!tileDev || !lutHost || !outDev) SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
     if (top < 0 || left < 0 || bottom > ysize || right > xsize || top > bottom || left > right) SSG_FAIL(ctx, SSG_ERR_ARG, "bad window");
+    SSG_TRY(ssg_scratch_reset(ctx));
     const size_t n = (size_t)maxId + 1;
     SSG_TRY(ssg_reserve(ctx, ctx->lut, n * sizeof(unsigned)));
     ctx->lutStage.assign(lutHost, lutHost + n);

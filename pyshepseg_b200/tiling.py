@@ -481,9 +481,26 @@ class TiledSegmenter(object):
                 return (a.ctypes.data, False)
         return None
 
+    def _reserve(self, slot, segments):
+        """Size a slot's device memory for the largest tile (or, for a slot that only stitches,
+        for the largest overlap strips) before the first tile: growing later would put cudaMalloc
+        and cudaFree, which synchronise the device, in the middle of the run."""
+        maxPix = max(t.xsize * t.ysize for t in self.tiles.values())
+        maxStrip = self.overlapSize * max(t.xsize + t.ysize for t in self.tiles.values())
+        dtype = self.src.dtype.newbyteorder('=')
+        direct = self._directSource() is not None
+        if segments:
+            # (with a directly addressable raster the tile image is gathered into the slot's own
+            # staging buffer, so the context's image buffer is not needed)
+            slot.ctx.call('ssg_ctx_reserve', maxPix, 0 if direct else len(self.bandNumbers),
+                _lib.DTYPE_CODES[numpy.dtype(dtype)], 0)
+        else:
+            slot.ctx.call('ssg_ctx_reserve', 0, 0, 0, maxStrip * 24 + (64 << 20))
+
     def _worker(self, slot, pool, inQue):
         """A segmentation worker (tiling.py:1560-1613): pops tiles until the queue is empty."""
         with slot.lock:
+            self._reserve(slot, True)
             before = slot.ctx.launch_count()
             self._profileStart(slot)
             while not self.forceExit.is_set():
@@ -606,6 +623,7 @@ class TiledSegmenter(object):
         main.lock.acquire()
         before = main.ctx.launch_count()
         try:
+            self._reserve(main, numWorkers == 0)
             self._profileStart(main)
             if numWorkers > 0:
                 inQue = queue.Queue()
@@ -698,7 +716,7 @@ class _DeviceHistogram(object):
     def ensure(self, ctx, n):
         if n <= self.cap:
             return
-        newCap = max(n, 2 * self.cap, 1 << 16)
+        newCap = max(n, 4 * self.cap, 1 << 20)
         p = ctx.dev_alloc(newCap * 8)
         ctx.call('ssg_memset_d', p, 0, newCap * 8)
         if self.dev is not None:

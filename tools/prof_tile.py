@@ -19,5 +19,21 @@ def main():
             rows, cols, bands, tm['total'], tm['assign'], tm['clump'], tm['single'], tm['small'],
             tm['numClumps'], res.segimg.max()), flush=True)
 
+    # per-kernel device time of one more run (events around every launch)
+    import ctypes
+    from pyshepseg_b200 import _lib
+    ctx = _lib.default_context()
+    ctx.call('ssg_profile_enable', 1)
+    shepseg.doShepherdSegmentation(img, minSegmentSize=50, kmeansObj=km)
+    buf = ctypes.create_string_buffer(1 << 16)
+    ctx.call('ssg_profile_fetch', buf, len(buf))
+    ctx.call('ssg_profile_enable', 0)
+    rows_ = [l.split() for l in buf.value.decode().splitlines()]
+    tot = sum(float(r[2]) for r in rows_)
+    for r in sorted(rows_, key=lambda r: -float(r[2])):
+        print('   %-34s x%-3s %8.3f ms  %5.1f%%' % (r[0], r[1], float(r[2]), 100 * float(r[2]) / tot))
+    print('   kernels total %.3f ms' % tot)
+
+
 if __name__ == '__main__':
     main()
