@@ -50,6 +50,7 @@ WORKLOAD = {
 }
 METRIC = 'Mpixels/sec full segmentation (assign+clump+eliminate+stitch), tiled 10980x10980x4 uint16'
 UNIT = 'Mpixel/s'
+E2E_WORKERS = int(os.environ.get('BENCH_E2E_WORKERS', '2'))   # segmentation workers of the host-to-host run
 
 # algorithmic bytes per pixel of the kernels:
 # what one launch must move at the very least, per pixel it processes
@@ -301,7 +302,7 @@ def run_ours(args, wl):
         return (seg, maxSegId)
 
     def step_e2e():
-        cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=2,
+        cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=E2E_WORKERS,
             devices=[local], tileCompletionTimeout=600)
         sink = rasterfile.MemorySink.__new__(rasterfile.MemorySink)
         sink.array = pinnedOut.array
@@ -430,7 +431,7 @@ def run_ours(args, wl):
             'config': workload_config(wl, args.gpus),
             'e2e': {'value': e2eValue, 'unit': UNIT, 'ms_per_step': msE2E / args.steps,
                 'h2d_bytes_per_step': int(segE2E.h2dBytes), 'd2h_bytes_per_step': int(segE2E.d2hBytes),
-                'workers': 2, 'same_labels_as_resident': sameMosaic},
+                'workers': E2E_WORKERS, 'same_labels_as_resident': sameMosaic},
             'gpu_launches': int(launchesResident),
             'roofline': roof, 'roofline_other': extra, 'kernels': kernels,
             'cpu_baseline': cpu, 'clocks': clocks,

@@ -214,6 +214,9 @@ class Context(object):
 
     # ---- device memory -------------------------------------------------------------------
     def dev_alloc(self, nbytes):
+        if os.environ.get('SSG_DEBUG_ALLOC'):
+            import sys
+            print('[ssg py] dev_alloc %d bytes' % nbytes, file=sys.stderr)
         p = ctypes.c_void_p()
         self.check(self.lib.ssg_dev_alloc(self.h, int(nbytes), ctypes.byref(p)), 'ssg_dev_alloc')
         return p.value

@@ -200,29 +200,25 @@ k_ccl_border(const int32_t *__restrict__ img, int64_t nRows, int64_t nCols, int3
     }
 }
 
-// ---- 3. flatten -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ccl_flatten(unsigned *label, int64_t N)
-{
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    unsigned l = label[p];
-    if (l == SSG_NIL) return;
-    unsigned r = g_find(label, l);
-    if (r != l) label[p] = r;
-}
-
-// ---- 4. numbering ---------------------------------------------------------------------------
-// a pixel is a root (the seed of a clump) iff it points at itself
+// ---- 3. flatten + 4a. count the roots ----------------------------------------------------------
+// every pixel points at its root; a pixel is a root (the seed of a clump) iff it points at
+// itself, which the flattening does not change, so the per-block root counts of the numbering
+// are taken in the same pass (thread = 4 consecutive pixels, block = NUM_BLOCK_PIX)
 __global__ void __launch_bounds__(256)
-k_count_roots(const unsigned *__restrict__ label, int64_t N, unsigned *__restrict__ blockCnt,
-              unsigned long long *counters)
+k_ccl_flatten_count(unsigned *label, int64_t N, unsigned *__restrict__ blockCnt,
+                    unsigned long long *counters)
 {
     const int64_t base = (int64_t)blockIdx.x * NUM_BLOCK_PIX + (int64_t)threadIdx.x * 4;
     int cnt = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        int64_t p = base + i;
-        if (p < N && label[p] == (unsigned)p) cnt++;
+        const int64_t p = base + i;
+        if (p >= N) break;
+        const unsigned l = label[p];
+        if (l == SSG_NIL) continue;
+        if (l == (unsigned)p) { cnt++; continue; }
+        const unsigned r = g_find(label, l);
+        if (r != l) label[p] = r;
     }
     __shared__ int wsum[8];
 #pragma unroll
@@ -345,7 +341,7 @@ k_count_oversized(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
 }
 
 // labels (root pointers) -> dense ids in seg + size table; returns the number of roots
-static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t nRows, int64_t nCols,
+static int number_from_labels(ssg_ctx *ctx, unsigned *label, int64_t nRows, int64_t nCols,
                               int four, unsigned clumpId, unsigned *seg, unsigned *numRoots,
                               bool listSingles)
 {
@@ -356,8 +352,8 @@ static int number_from_labels(ssg_ctx *ctx, const unsigned *label, int64_t nRows
     unsigned *blockCnt = bufp<unsigned>(ctx->blockCnt);
     unsigned *blockOff = blockCnt + nBlocks;
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_ROOTS, 0, sizeof(unsigned long long), ctx->stream));
-    SSG_PROF_BEGIN(ctx, "k_count_roots");
-    k_count_roots<<<(unsigned)nBlocks, 256, 0, ctx->stream>>>(label, N, blockCnt, counters);
+    SSG_PROF_BEGIN(ctx, "k_ccl_flatten_count");
+    k_ccl_flatten_count<<<(unsigned)nBlocks, 256, 0, ctx->stream>>>(label, N, blockCnt, counters);
     SSG_LAUNCHED(ctx);
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, blockCnt, blockOff, (int)nBlocks, ctx->stream));
@@ -509,9 +505,6 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
     if (nBorder > 0) {
         SSG_PROF_BEGIN(ctx, "k_ccl_border");
         k_ccl_border<<<gridFor(nBorder, 256), 256, 0, ctx->stream>>>(clusterDev, nRows, nCols, ignoreVal, four, label, nHB, nVB);
-        SSG_LAUNCHED(ctx);
-        SSG_PROF_BEGIN(ctx, "k_ccl_flatten");
-        k_ccl_flatten<<<gridFor(N, 256), 256, 0, ctx->stream>>>(label, N);
         SSG_LAUNCHED(ctx);
     }
     unsigned numRoots = 0;

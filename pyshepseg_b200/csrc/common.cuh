@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string>
 #include <vector>
@@ -182,6 +183,7 @@ static inline int ssg_reserve(ssg_ctx *ctx, DevBuf &b, size_t bytes)
             }
             ctx->spills.push_back(q);
             ctx->spillBytes += want;
+            if (getenv("SSG_DEBUG_ALLOC")) fprintf(stderr, "[ssg %p] scratch spill %zu bytes (slab %zu used of %zu)\n", (void *)ctx, want, ctx->slabUsed, ctx->slabCap);
             b.p = q;
         }
         b.cap = want;
@@ -195,6 +197,7 @@ static inline int ssg_reserve(ssg_ctx *ctx, DevBuf &b, size_t bytes)
         b.cap = 0;
     }
     size_t want = bytes + bytes / 8 + 256;   // a little headroom: tiles of one run vary in size
+    if (getenv("SSG_DEBUG_ALLOC")) fprintf(stderr, "[ssg %p] persistent buffer grows to %zu bytes\n", (void *)ctx, want);
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -229,6 +232,7 @@ static inline int ssg_scratch_reset(ssg_ctx *ctx, size_t atLeast = 0)
         ctx->slab = nullptr;
         ctx->slabCap = 0;
         size_t want = need + need / 8 + (1u << 20);
+        if (getenv("SSG_DEBUG_ALLOC")) fprintf(stderr, "[ssg %p] slab regrown to %zu bytes\n", (void *)ctx, want);
         void *q = nullptr;
         if (cudaMalloc(&q, want) != cudaSuccess) {
             cudaGetLastError();

@@ -326,24 +326,35 @@ k_finalize_sums(const unsigned long long *__restrict__ isum, const unsigned *__r
     if (lane_id() == 0 && m) atomicAdd(&counters[C_NUM_BIGSUM], (unsigned long long)__popc(m));
 }
 
-// ordered float32 chain for one (segment, band): s = RN32(s + x) in raster order
+// ordered float32 chain for one (segment, band): s = RN32(s + x) in raster order.  One warp
+// per chain: the lanes fetch 32 values at a time (the next batch is in flight while the
+// current one is added), the adds themselves run in order through shuffles.
 template <typename T>
 __global__ void __launch_bounds__(128)
 k_ordered_sums(const T *__restrict__ img, int nB, int64_t N, const unsigned *__restrict__ pixSorted,
                const unsigned *__restrict__ keysSorted, const unsigned *__restrict__ runStart,
                unsigned numRuns, int64_t M, float *fsum)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t run = t / nB;
-    const int b = (int)(t % nB);
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = lane_id();
+    const int64_t run = w / nB;
+    const int b = (int)(w % nB);
     if (run >= numRuns) return;
     const int64_t lo = runStart[run];
     const int64_t hi = (run + 1 < numRuns) ? (int64_t)runStart[run + 1] : M;
     const unsigned s = keysSorted[lo];
+    const T *plane = img + (size_t)b * N;
     float acc = 0.0f;
-    for (int64_t i = lo; i < hi; i++)
-        acc = __double2float_rn((double)acc + (double)img[(size_t)b * N + pixSorted[i]]);
-    fsum[(size_t)s * nB + b] = acc;
+    float next = (lo + lane < hi) ? (float)plane[pixSorted[lo + lane]] : 0.0f;
+    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+        const float cur = next;
+        const int64_t i1 = i0 + 32 + lane;
+        next = (i1 < hi) ? (float)plane[pixSorted[i1]] : 0.0f;
+        const int n = (int)((hi - i0) < 32 ? (hi - i0) : 32);
+        for (int k = 0; k < n; k++)
+            acc = __double2float_rn((double)acc + (double)__shfl_sync(0xffffffffu, cur, k));
+    }
+    if (lane == 0) fsum[(size_t)s * nB + b] = acc;
 }
 
 template <typename T>
@@ -376,7 +387,7 @@ static int build_spectra_t(ssg_ctx *ctx, const T *img, int nB, int64_t N, const 
         SSG_TRY(ssgk_group_pixels(ctx, seg, N, bigFlag, &pixSorted, &keysSorted, &runStart, &M, &numRuns));
         if (M > 0) {
             SSG_PROF_BEGIN(ctx, "k_ordered_sums");
-            k_ordered_sums<T><<<gridFor((int64_t)numRuns * nB, 128), 128, 0, ctx->stream>>>(
+            k_ordered_sums<T><<<gridFor((int64_t)numRuns * nB * 32, 128), 128, 0, ctx->stream>>>(
                 img, nB, N, pixSorted, keysSorted, runStart, numRuns, M, fsum);
             SSG_LAUNCHED(ctx);
         }

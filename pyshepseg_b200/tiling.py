@@ -328,12 +328,13 @@ class _Slot(object):
 
 class _GpuState(object):
     """Everything kept per device between calls: slot 0 is the stitch / sequential context,
-    slots 1.. are the segmentation workers; one pool of per-tile label buffers."""
+    slots 1.. are the segmentation workers; one pool of per-tile label buffers; the histogram."""
     def __init__(self, device):
         self.device = device
         self.slots = []
         self.pool = _DevicePool()
         self.lock = threading.Lock()
+        self.hist = _DeviceHistogram()
 
     def slot(self, i):
         with self.lock:
@@ -343,6 +344,7 @@ class _GpuState(object):
 
     def close(self):
         if self.slots:
+            self.hist.close(self.slots[0].ctx)
             self.pool.close(self.slots[0].ctx)
         for sl in self.slots:
             sl.close()
@@ -616,7 +618,7 @@ class TiledSegmenter(object):
         state = gpuState(self.device)
         pool = state.pool
         main = state.slot(0)
-        hist = _DeviceHistogram()
+        hist = state.hist
         offset = 0
         workers = []
         numWorkers = cfg.numWorkers if cfg.concurrencyType == CONC_THREADS else 0
@@ -624,6 +626,7 @@ class TiledSegmenter(object):
         before = main.ctx.launch_count()
         try:
             self._reserve(main, numWorkers == 0)
+            hist.reset(main.ctx)
             self._profileStart(main)
             if numWorkers > 0:
                 inQue = queue.Queue()
@@ -661,7 +664,6 @@ class TiledSegmenter(object):
                 th.join()
             try:
                 self._profileStop(main)
-                hist.close(main.ctx)
                 for t in self.tiles.values():
                     if t.buf is not None:
                         pool.put(t.buf)
@@ -724,6 +726,11 @@ class _DeviceHistogram(object):
             ctx.synchronize()
             ctx.dev_free(self.dev)
         (self.dev, self.cap) = (p, newCap)
+
+    def reset(self, ctx):
+        """Empty the histogram for a new run (the buffer is kept between runs)."""
+        if self.dev is not None:
+            ctx.call('ssg_memset_d', self.dev, 0, self.cap * 8)
 
     def fetch(self, ctx, n):
         h = numpy.zeros(n, dtype=numpy.uint64)
