@@ -1,0 +1,469 @@
+"""
+One mosaic, its tiles sharded over the GPUs of one box (one process per GPU, torch.distributed).
+
+The path shards by tile: every tile is segmented independently given the shared cluster
+centres (shepseg.doShepherdSegmentation per tile, tiling.py:1446/1586).  What the reference does
+sequentially afterwards (stitchTiles, tiling.py:950-1064: tile after tile in row-major order,
+carrying the running maxSegId and the recoded overlap strips of the finished neighbours) needs
+three small exchanges when the tiles live on different ranks:
+
+  strips   the LOCAL labels of an upper / left neighbour under a tile's overlap, when that
+           neighbour lives on another rank (device-to-device send/recv, NCCL over NVLink);
+  counts   one integer per tile, the highest rank among its self-numbered segments inside its
+           trimmed window: the id offset of tile t is the sum over the tiles before it (one
+           all-gather).  That is what the reference's "maxSegId = max(maxSegId, trimmed.max())"
+           (tiling.py:1042-1043) amounts to unless a window holds an inherited id above the
+           running maximum; the recurrence is checked on every tile after the resolve and the
+           ranks fall back to the sequential order over all tables if it fails anywhere, so the
+           result is the reference's in every case;
+  tables   the per-segment tables (rank, flags, votes) of the tiles whose final ids a tile on
+           another rank has to look up: a crossing segment takes the final id of the neighbour
+           segment it overlaps most (recodeSharedSegments, tiling.py:1128-1203), and that id may
+           in turn be inherited from the neighbour's neighbour.  Look-ups are lazy and per
+           entry, so no rank replays another rank's tiles.
+
+Everything here is host logic on numpy arrays; the device work is behind the `ops` object the
+caller hands in (tiling.TiledSegmenter for the GPU, plain numpy in the CPU tests).
+"""
+import io
+
+import numpy
+
+from . import _lib
+
+KEY_FLAGS = _lib.SEG_KEYTOP | _lib.SEG_KEYLEFT
+
+
+def rowMajor(tileInfo):
+    return sorted(tileInfo.tiles.keys(), key=lambda cr: (cr[1], cr[0]))
+
+
+def partitionTiles(tileInfo, world):
+    """
+    owner rank of every tile: contiguous chunks of the row-major tile list (tiling.py:892-893)
+    with as equal a share of the tile pixels as the tile boundaries allow.  Contiguous chunks
+    keep most neighbours on the same GPU.
+    """
+    order = rowMajor(tileInfo)
+    pix = numpy.array([tileInfo.tiles[cr][2] * tileInfo.tiles[cr][3] for cr in order], dtype=numpy.float64)
+    cum = numpy.cumsum(pix)
+    total = cum[-1]
+    owner = {}
+    for (i, cr) in enumerate(order):
+        mid = cum[i] - pix[i] / 2.0          # the rank whose share holds the tile's midpoint
+        owner[cr] = min(world - 1, int(mid * world / total))
+    # a rank must not be skipped: make the assignment monotone and gap-free
+    last = 0
+    for cr in order:
+        r = owner[cr]
+        if r > last + 1:
+            r = last + 1
+        owner[cr] = r
+        last = r
+    return owner
+
+
+class TileTable(object):
+    """The host copy of what ssg_tile_tables_device computed for one tile."""
+    def __init__(self, maxId, countNew, rank, flags, pairKeys, pairCounts):
+        self.maxId = int(maxId)
+        self.countNew = int(countNew)
+        self.rank = numpy.ascontiguousarray(rank, dtype=numpy.uint32)
+        self.flags = numpy.ascontiguousarray(flags, dtype=numpy.uint8)
+        self.pairKeys = numpy.ascontiguousarray(pairKeys, dtype=numpy.uint64)
+        self.pairCounts = numpy.ascontiguousarray(pairCounts, dtype=numpy.uint32)
+        self._split = None
+
+    @property
+    def maxRankInTrim(self):
+        sel = (self.flags & (_lib.SEG_NUMBERED | _lib.SEG_INTRIM)) == (_lib.SEG_NUMBERED | _lib.SEG_INTRIM)
+        return int(self.rank[sel].max()) if sel.any() else 0
+
+    @property
+    def maxLabelInTrim(self):
+        sel = numpy.flatnonzero(self.flags & _lib.SEG_INTRIM)
+        return int(sel[-1]) if len(sel) else 0
+
+    def pairs(self):
+        """(isLeft, segment, neighbour label, count) of the votes, decoded once."""
+        if self._split is None:
+            k = self.pairKeys
+            self._split = ((k >> numpy.uint64(63)) != 0,
+                ((k >> numpy.uint64(32)) & numpy.uint64(0x7FFFFFFF)).astype(numpy.int64),
+                (k & numpy.uint64(0xFFFFFFFF)).astype(numpy.int64),
+                self.pairCounts.astype(numpy.int64))
+        return self._split
+
+    def pack(self):
+        buf = io.BytesIO()
+        buf.write(numpy.array([self.maxId, self.countNew, len(self.rank), len(self.pairKeys)],
+            dtype=numpy.int64).tobytes())
+        for a in (self.pairKeys, self.rank, self.pairCounts, self.flags):   # widest first: aligned
+            buf.write(a.tobytes())
+        return buf.getvalue()
+
+    @staticmethod
+    def unpack(b):
+        hdr = numpy.frombuffer(b, dtype=numpy.int64, count=4)
+        (maxId, countNew, n, m) = (int(v) for v in hdr)
+        o = 32
+        pairKeys = numpy.frombuffer(b, dtype=numpy.uint64, count=m, offset=o)
+        o += 8 * m
+        rank = numpy.frombuffer(b, dtype=numpy.uint32, count=n, offset=o)
+        o += 4 * n
+        pairCounts = numpy.frombuffer(b, dtype=numpy.uint32, count=m, offset=o)
+        o += 4 * m
+        flags = numpy.frombuffer(b, dtype=numpy.uint8, count=n, offset=o)
+        return TileTable(maxId, countNew, rank, flags, pairKeys, pairCounts)
+
+
+def packTables(tables):
+    """{tile: TileTable} -> bytes (for an all-gather of byte buffers)."""
+    buf = io.BytesIO()
+    buf.write(numpy.array([len(tables)], dtype=numpy.int64).tobytes())
+    for (cr, tb) in sorted(tables.items()):
+        body = tb.pack()
+        pad = (-len(body)) % 8
+        buf.write(numpy.array([cr[0], cr[1], len(body) + pad], dtype=numpy.int64).tobytes())
+        buf.write(body)
+        buf.write(b'\0' * pad)
+    return buf.getvalue()
+
+
+def unpackTables(b):
+    b = bytes(b)
+    n = int(numpy.frombuffer(b, dtype=numpy.int64, count=1)[0])
+    o = 8
+    out = {}
+    for _ in range(n):
+        (c, r, size) = (int(v) for v in numpy.frombuffer(b, dtype=numpy.int64, count=3, offset=o))
+        o += 24
+        out[(c, r)] = TileTable.unpack(b[o:o + size])
+        o += size
+    return out
+
+
+class MissingTable(Exception):
+    """a look-up reached a tile whose table this rank does not hold"""
+
+
+class LazyResolver(object):
+    """
+    Final ids from per-tile tables when the id offsets are known up front (offset of a tile = sum
+    of countNew over the tiles before it).  lut entries are computed on demand:
+      numbered segment           offset + rank                       (tiling.py:1264-1267)
+      crossing segment           the mode of the final ids of the neighbour's labels under it,
+                                 smallest id on ties, top overlap first, left overriding
+                                 (tiling.py:1107-1121, 1194)
+      anything else, and 0       0 (the segment belongs to a neighbour, tiling.py:1241)
+    """
+    UNKNOWN = numpy.uint32(0xFFFFFFFF)
+
+    def __init__(self, tables, offsets, simple=False):
+        self.tables = tables
+        self.offsets = offsets
+        self.simple = simple
+        self.luts = {}
+        self.missing = set()    # tiles a look-up reached without their table being here
+
+    def _lutOf(self, cr):
+        if cr not in self.luts:
+            if cr not in self.tables:
+                raise MissingTable(cr)
+            self.luts[cr] = numpy.full(self.tables[cr].maxId + 1, self.UNKNOWN, dtype=numpy.uint32)
+        return self.luts[cr]
+
+    def reset(self):
+        self.luts = {}
+        self.missing = set()
+
+    def finalIds(self, cr, labels):
+        """final ids of the given local labels of tile cr (int64 array, any shape)"""
+        from .tiling import _modeByKey
+        lut = self._lutOf(cr)
+        labels = numpy.asarray(labels, dtype=numpy.int64)
+        need = numpy.unique(labels[lut[labels] == self.UNKNOWN])
+        if len(need) > 0:
+            tb = self.tables[cr]
+            off = self.offsets[cr]
+            if self.simple:
+                lut[need] = numpy.where(need > 0, need + off, 0).astype(numpy.uint32)
+            else:
+                fl = tb.flags[need]
+                vals = numpy.zeros(len(need), dtype=numpy.uint32)
+                numbered = (fl & _lib.SEG_NUMBERED) != 0
+                vals[numbered] = tb.rank[need[numbered]] + numpy.uint32(off)
+                lut[need] = vals
+                keyed = need[(fl & KEY_FLAGS) != 0]
+                if len(keyed) > 0 and len(tb.pairKeys) > 0:
+                    (isLeft, segs, nbr, counts) = tb.pairs()
+                    wanted = numpy.zeros(tb.maxId + 1, dtype=bool)
+                    wanted[keyed] = True
+                    mine = wanted[segs]
+                    for (sel, nb) in ((mine & ~isLeft, (cr[0], cr[1] - 1)), (mine & isLeft, (cr[0] - 1, cr[1]))):
+                        if not sel.any():
+                            continue
+                        try:
+                            mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
+                        except MissingTable as e:
+                            # noted; the caller fetches the table and resolves again
+                            self.missing.add(e.args[0])
+                            continue
+                        (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
+                        lut[k] = mode.astype(numpy.uint32)
+        return lut[labels]
+
+    def fullLut(self, cr):
+        n = self.tables[cr].maxId + 1
+        return self.finalIds(cr, numpy.arange(n, dtype=numpy.int64))
+
+
+def sequentialResolve(order, tables, simple=False):
+    """The reference's order, tile after tile (tiling.resolveTile); returns (luts, offsets, maxSegId)."""
+    from .tiling import resolveTile
+    luts = {}
+    offsets = {}
+    offset = 0
+    for cr in order:
+        tb = tables[cr]
+        offsets[cr] = offset
+        t = _lib.TileTables()
+        t.maxId = tb.maxId
+        t.countNew = tb.countNew
+        t.numPairs = len(tb.pairKeys)
+        (lut, trimmedMax) = resolveTile(t, tb.rank, tb.flags, tb.pairKeys, tb.pairCounts, offset,
+            luts.get((cr[0], cr[1] - 1)), luts.get((cr[0] - 1, cr[1])), simple)
+        luts[cr] = lut
+        offset = max(offset, trimmedMax)
+    return (luts, offsets, offset)
+
+
+class LocalComm(object):
+    """world of one (and the interface the real communicators implement)"""
+    rank = 0
+    world = 1
+
+    def allgatherInts(self, values):
+        """list of ints from every rank -> list (per rank) of lists"""
+        return [list(values)]
+
+    def allgatherBytes(self, b):
+        return [bytes(b)]
+
+    def exchange(self, sends, recvs):
+        """sends: [(dstRank, tensor)], recvs: [(srcRank, tensor)] in matching order per rank pair"""
+        assert not sends and not recvs
+
+    def allreduceSum(self, array):
+        return array
+
+
+class TorchComm(object):
+    """torch.distributed process group (nccl on the GPUs, gloo in the CPU tests)"""
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.device = device if device is not None else torch.device('cpu')
+
+    def _t(self, a):
+        return self.torch.from_numpy(numpy.ascontiguousarray(a)).to(self.device)
+
+    def allgatherInts(self, values):
+        n = self._t(numpy.array([len(values)], dtype=numpy.int64))
+        sizes = [self.torch.zeros_like(n) for _ in range(self.world)]
+        self.dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(sizes) if sizes else 0
+        mine = numpy.zeros(max(m, 1), dtype=numpy.int64)
+        mine[:len(values)] = values
+        mine = self._t(mine)
+        out = [self.torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine)
+        return [o.cpu().numpy()[:sizes[i]].tolist() for (i, o) in enumerate(out)]
+
+    def allgatherBytes(self, b):
+        sizes = [s[0] for s in self.allgatherInts([len(b)])]
+        m = max(max(sizes), 1)
+        mine = numpy.zeros(m, dtype=numpy.uint8)
+        mine[:len(b)] = numpy.frombuffer(b, dtype=numpy.uint8)
+        mine = self._t(mine)
+        out = [self.torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine)
+        return [o.cpu().numpy()[:sizes[i]].tobytes() for (i, o) in enumerate(out)]
+
+    def exchange(self, sends, recvs):
+        ops = []
+        for (dst, t) in sends:
+            ops.append(self.dist.P2POp(self.dist.isend, t, dst))
+        for (src, t) in recvs:
+            ops.append(self.dist.P2POp(self.dist.irecv, t, src))
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.device.type == 'cuda':
+            self.torch.cuda.synchronize(self.device)
+
+    def allreduceSum(self, array):
+        t = self._t(array)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+
+class ShardedStitch(object):
+    """
+    The stitch of a mosaic whose tiles are spread over the ranks of `comm`.  The caller has
+    segmented its own tiles and provides `ops`:
+
+      ops.sendStrip(cr, which)            the LOCAL labels of tile cr's bottom ('bottom': last
+                                          overlap rows) or right ('right': last overlap columns)
+                                          strip as a contiguous tensor to send
+      ops.recvStrip(cr, which, shape)     a tensor to receive such a strip of a remote tile into
+      ops.tables(cr, top, left)           TileTable of own tile cr; top / left are None (no such
+                                          neighbour), 'local' (the neighbour is an own tile) or
+                                          the tensor received for it
+      ops.apply(cr, lut, table)           write lut[tile] over the trimmed window of own tile cr
+    """
+    def __init__(self, tileInfo, overlapSize, simple, comm):
+        self.tileInfo = tileInfo
+        self.overlap = int(overlapSize)
+        self.simple = simple
+        self.comm = comm
+        self.order = rowMajor(tileInfo)
+        self.owner = partitionTiles(tileInfo, comm.world)
+        self.mine = [cr for cr in self.order if self.owner[cr] == comm.rank]
+        self.usedFallback = False
+        self.forceSequential = False    # (tests) take the fall-back even if the check passes
+
+    def neighbours(self, cr):
+        (c, r) = cr
+        up = (c, r - 1) if r > 0 else None
+        left = (c - 1, r) if c > 0 else None
+        return (up, left)
+
+    def stripPlan(self):
+        """(sends, recvs) of this rank as lists of (peerRank, tile, which, shape), in the
+        row-major order of the receiving tile (both sides enumerate the same order)."""
+        sends = []
+        recvs = []
+        ov = self.overlap
+        if self.simple:
+            return (sends, recvs)
+        for cr in self.order:
+            (xpos, ypos, xsize, ysize) = self.tileInfo.tiles[cr]
+            (up, left) = self.neighbours(cr)
+            for (nb, which) in ((up, 'bottom'), (left, 'right')):
+                if nb is None or self.owner[nb] == self.owner[cr]:
+                    continue
+                (nx, ny, nxs, nys) = self.tileInfo.tiles[nb]
+                shape = (ov, nxs) if which == 'bottom' else (nys, ov)
+                if self.owner[nb] == self.comm.rank:
+                    sends.append((self.owner[cr], nb, which, shape))
+                if self.owner[cr] == self.comm.rank:
+                    recvs.append((self.owner[nb], nb, which, shape))
+        return (sends, recvs)
+
+    def run(self, ops):
+        """returns (maxSegId, offsets of all tiles, luts of own tiles)"""
+        comm = self.comm
+        # 1. strips of remote neighbours
+        (sends, recvs) = self.stripPlan()
+        received = {}
+        sendList = [(peer, ops.sendStrip(cr, which)) for (peer, cr, which, shape) in sends]
+        recvList = []
+        for (peer, cr, which, shape) in recvs:
+            t = ops.recvStrip(cr, which, shape)
+            received[(cr, which)] = t
+            recvList.append((peer, t))
+        comm.exchange(sendList, recvList)
+
+        # 2. tables of own tiles
+        tables = {}
+        for cr in self.mine:
+            (up, left) = self.neighbours(cr)
+            top = lf = None
+            if not self.simple:
+                if up is not None:
+                    top = 'local' if self.owner[up] == comm.rank else received[(up, 'bottom')]
+                if left is not None:
+                    lf = 'local' if self.owner[left] == comm.rank else received[(left, 'right')]
+            tables[cr] = ops.tables(cr, top, lf)
+
+        # 3. offsets.  The reference moves the running maximum on tile after tile:
+        # maxSegId = max(maxSegId, trimmed.max()) (tiling.py:1042-1043).  Inside the trimmed
+        # window a tile has its own numbered segments (offset + rank) and segments recoded to ids
+        # of EARLIER tiles; unless one of those carries an id above the running maximum (a
+        # neighbour's segment that was numbered without having a pixel in its own trimmed
+        # window), the maximum moves on by the highest rank present in the window.  Take that as
+        # the hypothesis -- offsets = running sum of one integer per tile, known to every rank
+        # after one all-gather -- resolve, and check the recurrence on every tile afterwards.
+        mineInts = []
+        for cr in self.mine:
+            tb = tables[cr]
+            step = tb.maxLabelInTrim if self.simple else tb.maxRankInTrim
+            mineInts += [cr[0], cr[1], step]
+        steps = {}
+        for vals in comm.allgatherInts(mineInts):
+            for i in range(0, len(vals), 3):
+                steps[(vals[i], vals[i + 1])] = vals[i + 2]
+        offsets = {}
+        offset = 0
+        for cr in self.order:
+            offsets[cr] = offset
+            offset += steps[cr]
+        maxSegId = offset
+
+        # 4. final ids of own tiles.  Tables of the tiles that a tile on another rank looks into
+        # are fetched on request: first the direct neighbours across a rank boundary, then
+        # whatever the look-ups ask for beyond them (a crossing segment's id can be inherited
+        # through several tiles around a corner).
+        luts = {}
+        known = dict(tables)
+        want = set()
+        if not self.simple:
+            for cr in self.mine:
+                for nb in self.neighbours(cr):
+                    if nb is not None and self.owner[nb] != comm.rank:
+                        want.add(nb)
+        resolver = LazyResolver(known, offsets, self.simple)
+        for _round in range(len(self.order) + 2):
+            asked = set()
+            for vals in comm.allgatherInts([v for cr in sorted(want) for v in cr]):
+                asked.update((vals[i], vals[i + 1]) for i in range(0, len(vals), 2))
+            if asked:
+                give = dict((cr, tables[cr]) for cr in asked if cr in tables)
+                for b in comm.allgatherBytes(packTables(give)):
+                    for (cr, tb) in unpackTables(b).items():
+                        known.setdefault(cr, tb)
+            elif luts:
+                break
+            resolver.reset()
+            for cr in self.mine:
+                luts[cr] = resolver.fullLut(cr)
+            want = set(resolver.missing)
+        else:
+            raise RuntimeError('sharded stitch: table look-ups did not settle')
+        # the check of the hypothesis
+        ok = 1
+        for cr in self.mine:
+            inTrim = (tables[cr].flags & _lib.SEG_INTRIM) != 0
+            trimmedMax = int(luts[cr][inTrim].max()) if inTrim.any() else 0
+            if max(offsets[cr], trimmedMax) != offsets[cr] + steps[cr] or self.forceSequential:
+                ok = 0
+        if min(v[0] for v in comm.allgatherInts([ok])) == 0:
+            # some window holds an inherited id above the running maximum: replay the
+            # reference's sequential order over all tables, on every rank
+            self.usedFallback = True
+            known = {}
+            for b in comm.allgatherBytes(packTables(tables)):
+                known.update(unpackTables(b))
+            (allLuts, offsets, maxSegId) = sequentialResolve(self.order, known, self.simple)
+            luts = dict((cr, allLuts[cr]) for cr in self.mine)
+
+        # 5. apply
+        for cr in self.mine:
+            ops.apply(cr, luts[cr], tables[cr])
+        return (maxSegId, offsets, luts)

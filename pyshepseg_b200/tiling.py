@@ -436,6 +436,7 @@ class TiledSegmenter(object):
         nB = len(self.bandNumbers)
         nPix = tile.ysize * tile.xsize
         direct = self._directSource()
+        ypos = tile.ypos - getattr(self.src, 'yoff', 0)   # a rank of a sharded run holds a row band
         with self.timings.interval('reading'):
             if direct is not None:
                 # the raster is addressable memory (HBM, or host memory that cudaMemcpy2D can
@@ -445,13 +446,13 @@ class TiledSegmenter(object):
                 copy = 'ssg_memcpy2d_d2d' if onDevice else 'ssg_memcpy2d_h2d'
                 for (i, b) in enumerate(self.bandNumbers):
                     srcPtr = base + ((b - 1) * self.src.ysize * self.src.xsize +
-                        tile.ypos * self.src.xsize + tile.xpos) * item
+                        ypos * self.src.xsize + tile.xpos) * item
                     ctx.call(copy, imgDev + i * nPix * item, tile.xsize * item, srcPtr,
                         self.src.xsize * item, tile.xsize * item, tile.ysize)
             else:
                 with self.readSemaphore:
                     img = slot.pinnedFor(nB * nPix, dtype).reshape(nB, tile.ysize, tile.xsize)
-                    self.src.readWindow(self.bandNumbers, tile.xpos, tile.ypos, tile.xsize, tile.ysize,
+                    self.src.readWindow(self.bandNumbers, tile.xpos, ypos, tile.xsize, tile.ysize,
                         out=img)
         with self.timings.interval('segmentation'):
             if direct is None:
@@ -539,52 +540,46 @@ class TiledSegmenter(object):
                 ent[1] += float(ms)
 
     # ---- the stitch of one tile (main thread) ------------------------------------------------
-    def stitchOne(self, slot, pool, tile, offset, sink, hist):
+    def tileTables(self, slot, tile, topB, topStride, leftB, leftStride):
+        """Device phase 1 of the stitch for one tile + the copy of its tables to the host.
+        topB / leftB: device pointers of the neighbours' LOCAL labels under the overlaps."""
         ctx = slot.ctx
-        ti = self.tileInfo
-        (top, bottom, left, right) = tileMargins(ti, tile.col, tile.row, tile.xsize, tile.ysize,
-            self.overlapSize)
-        ov = self.overlapSize
-        up = self.tiles.get((tile.col, tile.row - 1)) if tile.row > 0 else None
-        lf = self.tiles.get((tile.col - 1, tile.row)) if tile.col > 0 else None
-        topB = leftB = None
-        (topStride, leftStride) = (0, 0)
-        if not self.simple:
-            if up is not None:      # the upper tile's bottom `ov` rows (its LOCAL labels)
-                topB = up.buf[1] + (up.ysize - ov) * up.xsize * 4
-                topStride = up.xsize
-            if lf is not None:      # the left tile's right `ov` columns
-                leftB = lf.buf[1] + (lf.xsize - ov) * 4
-                leftStride = lf.xsize
+        (top, bottom, left, right) = tileMargins(self.tileInfo, tile.col, tile.row, tile.xsize,
+            tile.ysize, self.overlapSize)
         tables = _lib.TileTables()
         with self.timings.interval('stitch_tables'):
-            ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, ov, topB, topStride,
-                leftB, leftStride, top, bottom, left, right, tile.numSegments, ctypes.byref(tables))
-        n = int(tables.maxId) + 1
-        rank = numpy.empty(n, dtype=numpy.uint32)
-        flags = numpy.empty(n, dtype=numpy.uint8)
-        pairKeys = numpy.empty(int(tables.numPairs), dtype=numpy.uint64)
-        pairCounts = numpy.empty(int(tables.numPairs), dtype=numpy.uint32)
-        ctx.call('ssg_tile_tables_fetch', _lib.ptr(rank), _lib.ptr(flags), _lib.ptr(pairKeys),
-            _lib.ptr(pairCounts))
-        with self.timings.interval('stitch_resolve'):
-            (lut, trimmedMax) = resolveTile(tables, rank, flags, pairKeys, pairCounts, offset,
-                None if up is None else up.lut, None if lf is None else lf.lut, self.simple)
-        tile.lut = lut
-        # final ids over the trimmed window, on the device, then to the output raster
+            ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, self.overlapSize,
+                topB, topStride, leftB, leftStride, top, bottom, left, right, tile.numSegments,
+                ctypes.byref(tables))
+            n = int(tables.maxId) + 1
+            rank = numpy.empty(n, dtype=numpy.uint32)
+            flags = numpy.empty(n, dtype=numpy.uint8)
+            pairKeys = numpy.empty(int(tables.numPairs), dtype=numpy.uint64)
+            pairCounts = numpy.empty(int(tables.numPairs), dtype=numpy.uint32)
+            ctx.call('ssg_tile_tables_fetch', _lib.ptr(rank), _lib.ptr(flags), _lib.ptr(pairKeys),
+                _lib.ptr(pairCounts))
+        self.d2hBytes += rank.nbytes + flags.nbytes + pairKeys.nbytes + pairCounts.nbytes
+        from . import distributed
+        return distributed.TileTable(tables.maxId, tables.countNew, rank, flags, pairKeys, pairCounts)
+
+    def applyLut(self, slot, tile, lut, maxId, sink, hist, histLen):
+        """Device phase 2: final ids over the trimmed window, on the device, then to the sink."""
+        ctx = slot.ctx
+        (top, bottom, left, right) = tileMargins(self.tileInfo, tile.col, tile.row, tile.xsize,
+            tile.ysize, self.overlapSize)
         (wr, wc) = (bottom - top, right - left)
-        hist.ensure(ctx, max(offset + int(tables.countNew), trimmedMax, int(lut.max()) if n else 0) + 1)
+        hist.ensure(ctx, histLen)
         xout = tile.xpos + left
-        yout = tile.ypos + top
+        yout = tile.ypos + top - getattr(sink, 'yoff', 0)
         if isinstance(sink, DeviceMosaicSink):
             # the mosaic lives in HBM: write the window in place
             ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
-                int(tables.maxId), top, bottom, left, right,
+                int(maxId), top, bottom, left, right,
                 sink.devPtr + (yout * sink.xsize + xout) * 4, sink.xsize, hist.dev, hist.cap)
         else:
             (window, winDev) = slot.windowFor(wr * wc)
             ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
-                int(tables.maxId), top, bottom, left, right, winDev, wc, hist.dev, hist.cap)
+                int(maxId), top, bottom, left, right, winDev, wc, hist.dev, hist.cap)
             arr = getattr(sink, 'array', None)
             if (type(sink) is rasterfile.MemorySink and isinstance(arr, numpy.ndarray) and
                     arr.flags.c_contiguous and arr.dtype == numpy.uint32):
@@ -597,8 +592,31 @@ class TiledSegmenter(object):
                 sink.write(out, xout, yout)
                 sink.writeOverviews(out, xout, yout)
             self.d2hBytes += wr * wc * 4
-        self.d2hBytes += rank.nbytes + flags.nbytes + pairKeys.nbytes + pairCounts.nbytes
         self.h2dBytes += lut.nbytes
+
+    def stitchOne(self, slot, pool, tile, offset, sink, hist):
+        ov = self.overlapSize
+        up = self.tiles.get((tile.col, tile.row - 1)) if tile.row > 0 else None
+        lf = self.tiles.get((tile.col - 1, tile.row)) if tile.col > 0 else None
+        topB = leftB = None
+        (topStride, leftStride) = (0, 0)
+        if not self.simple:
+            if up is not None:      # the upper tile's bottom `ov` rows (its LOCAL labels)
+                topB = up.buf[1] + (up.ysize - ov) * up.xsize * 4
+                topStride = up.xsize
+            if lf is not None:      # the left tile's right `ov` columns
+                leftB = lf.buf[1] + (lf.xsize - ov) * 4
+                leftStride = lf.xsize
+        tb = self.tileTables(slot, tile, topB, topStride, leftB, leftStride)
+        tables = _lib.TileTables()
+        (tables.maxId, tables.countNew, tables.numPairs) = (tb.maxId, tb.countNew, len(tb.pairKeys))
+        with self.timings.interval('stitch_resolve'):
+            (lut, trimmedMax) = resolveTile(tables, tb.rank, tb.flags, tb.pairKeys, tb.pairCounts, offset,
+                None if up is None else up.lut, None if lf is None else lf.lut, self.simple)
+        tile.lut = lut
+        n = tb.maxId + 1
+        self.applyLut(slot, tile, lut, tb.maxId, sink, hist,
+            max(offset + tb.countNew, trimmedMax, int(lut.max()) if n else 0) + 1)
         # the neighbours' labels are no longer needed once both users have run
         for nb in (up, lf):
             if nb is not None:
@@ -612,8 +630,12 @@ class TiledSegmenter(object):
         return max(offset, trimmedMax)
 
     # ---- driver ----------------------------------------------------------------------------
-    def run(self, sink):
-        """Segment and stitch every tile; returns (maxSegId, histogram)."""
+    def run(self, sink, comm=None):
+        """Segment and stitch every tile; returns (maxSegId, histogram).  With a communicator of
+        more than one rank (distributed.TorchComm) the tiles are shared out over the ranks and
+        `sink` receives this rank's trimmed windows only."""
+        if comm is not None and comm.world > 1:
+            return self.runSharded(sink, comm)
         cfg = self.cfg
         state = gpuState(self.device)
         pool = state.pool
@@ -674,12 +696,121 @@ class TiledSegmenter(object):
         return (offset, histogram)
 
 
+    def runSharded(self, sink, comm):
+        """
+        The tiles of the mosaic dealt over the ranks of `comm` (distributed.ShardedStitch): this
+        rank segments its own tiles, keeps their labels in HBM, exchanges overlap strips with the
+        ranks that own neighbouring tiles, and writes the trimmed windows of its tiles.
+        Returns (maxSegId, histogram summed over the ranks).
+        """
+        from . import distributed
+        import torch
+        cfg = self.cfg
+        state = gpuState(self.device)
+        pool = state.pool
+        main = state.slot(0)
+        hist = state.hist
+        stitch = distributed.ShardedStitch(self.tileInfo, self.overlapSize, self.simple, comm)
+        mine = stitch.mine
+        numWorkers = cfg.numWorkers if cfg.concurrencyType == CONC_THREADS else 0
+        workers = []
+        ov = self.overlapSize
+        cudaDev = torch.device('cuda', self.device)
+        seg = self
+
+        class Ops(object):
+            def sendStrip(self, cr, which):
+                t = seg.tiles[cr]
+                if which == 'bottom':
+                    out = torch.empty((ov, t.xsize), dtype=torch.int32, device=cudaDev)
+                    main.ctx.call('ssg_memcpy_d2d', out.data_ptr(), t.buf[1] + (t.ysize - ov) * t.xsize * 4,
+                        ov * t.xsize * 4)
+                else:
+                    out = torch.empty((t.ysize, ov), dtype=torch.int32, device=cudaDev)
+                    main.ctx.call('ssg_memcpy2d_d2d', out.data_ptr(), ov * 4, t.buf[1] + (t.xsize - ov) * 4,
+                        t.xsize * 4, ov * 4, t.ysize)
+                main.ctx.synchronize()
+                return out
+
+            def recvStrip(self, cr, which, shape):
+                return torch.empty(shape, dtype=torch.int32, device=cudaDev)
+
+            def tables(self, cr, top, left):
+                t = seg.tiles[cr]
+                (topB, topStride, leftB, leftStride) = (None, 0, None, 0)
+                if top is not None:
+                    if isinstance(top, str):
+                        up = seg.tiles[(t.col, t.row - 1)]
+                        (topB, topStride) = (up.buf[1] + (up.ysize - ov) * up.xsize * 4, up.xsize)
+                    else:
+                        (topB, topStride) = (top.data_ptr(), top.shape[1])
+                if left is not None:
+                    if isinstance(left, str):
+                        lf = seg.tiles[(t.col - 1, t.row)]
+                        (leftB, leftStride) = (lf.buf[1] + (lf.xsize - ov) * 4, lf.xsize)
+                    else:
+                        (leftB, leftStride) = (left.data_ptr(), left.shape[1])
+                return seg.tileTables(main, t, topB, topStride, leftB, leftStride)
+
+            def apply(self, cr, lut, tb):
+                t = seg.tiles[cr]
+                t.lut = lut
+                seg.applyLut(main, t, lut, tb.maxId, sink, hist, int(lut.max()) + 1 if len(lut) else 1)
+
+        main.lock.acquire()
+        before = main.ctx.launch_count()
+        try:
+            self._reserve(main, numWorkers == 0)
+            hist.reset(main.ctx)
+            self._profileStart(main)
+            with self.timings.interval('segmentation_all'):
+                if numWorkers > 0:
+                    inQue = queue.Queue()
+                    for cr in mine:
+                        inQue.put(cr)
+                    for w in range(numWorkers):
+                        th = threading.Thread(target=self._worker, args=(state.slot(1 + w), pool, inQue),
+                            daemon=True)
+                        th.start()
+                        workers.append(th)
+                    for th in workers:
+                        th.join()
+                    for cr in mine:
+                        if self.tiles[cr].error is not None:
+                            raise PyShepSegTilingError("A segmentation worker failed on tile col={} row={}: {}".format(
+                                cr[0], cr[1], self.tiles[cr].error))
+                else:
+                    for cr in mine:
+                        self.segmentOne(main, pool, self.tiles[cr])
+            with self.timings.interval('stitchtiles'):
+                (maxSegId, offsets, luts) = stitch.run(Ops())
+                histogram = hist.fetch(main.ctx, maxSegId + 1)
+                histogram = comm.allreduceSum(histogram)
+            self.d2hBytes += histogram.nbytes
+            self.usedFallback = stitch.usedFallback
+        finally:
+            self.forceExit.set()
+            for th in workers:
+                th.join()
+            try:
+                self._profileStop(main)
+                for t in self.tiles.values():
+                    if t.buf is not None:
+                        pool.put(t.buf)
+                        t.buf = None
+                self.launches += main.ctx.launch_count() - before
+            finally:
+                main.lock.release()
+        return (maxSegId, histogram)
+
+
 class DeviceRaster(rasterfile.RasterSource):
     """A band-sequential (count, ysize, xsize) raster that already lives in GPU memory
     (devPtr is a device pointer on the segmenting GPU).  Used to measure the path with its
     input resident in HBM; tiles are gathered with device-to-device copies."""
-    def __init__(self, devPtr, count, ysize, xsize, dtype, nodata=None):
+    def __init__(self, devPtr, count, ysize, xsize, dtype, nodata=None, yoff=0):
         self.devPtr = int(devPtr)
+        self.yoff = int(yoff)        # mosaic row of the buffer's first row (a rank's row band)
         (self.count, self.ysize, self.xsize) = (int(count), int(ysize), int(xsize))
         self.dtype = numpy.dtype(dtype)
         self.nodata = [nodata] * self.count
@@ -688,9 +819,10 @@ class DeviceRaster(rasterfile.RasterSource):
 class DeviceMosaicSink(rasterfile.RasterSink):
     """A uint32 (ysize, xsize) output mosaic in GPU memory: the stitch writes the trimmed
     windows in place and nothing but the small per-tile tables crosses PCIe."""
-    def __init__(self, devPtr, xsize, ysize):
+    def __init__(self, devPtr, xsize, ysize, yoff=0):
         self.devPtr = int(devPtr)
         (self.xsize, self.ysize) = (int(xsize), int(ysize))
+        self.yoff = int(yoff)        # mosaic row of the buffer's first row (a rank's row band)
         self.metadata = {}
         self.hist = None
 
