@@ -239,21 +239,30 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(wl, gpus):
-    return {'workload': wl['name'], 'raster': [wl['bands'], wl['rows'], wl['cols']], 'dtype': 'uint16',
-        'tileSize': wl['tileSize'], 'overlapSize': wl['overlapSize'], 'tiles': '2x2 (4096, 7908)',
+def workload_config(wl, gpus, shape=None, tileInfo=None):
+    (gr, gc) = SCENE_GRID.get(gpus, (1, gpus))
+    (nR, nC) = shape if shape is not None else (wl['rows'] * gr, wl['cols'] * gc)
+    name = wl['name'] if gpus == 1 else '%s_mosaic_of_%dx%d_scenes' % (wl['name'], gr, gc)
+    tiles = ('%dx%d' % (tileInfo.nrows, tileInfo.ncols)) if tileInfo is not None else None
+    return {'workload': name, 'raster': [wl['bands'], nR, nC], 'dtype': 'uint16',
+        'tileSize': wl['tileSize'], 'overlapSize': wl['overlapSize'], 'tiles': tiles,
         'numClusters': wl['numClusters'], 'minSegmentSize': wl['minSegmentSize'],
         'maxSpectralDiff': wl['maxSpectralDiff'], 'fourConnected': wl['fourConnected'],
-        'scenes': gpus, 'parallelism': 'one scene per GPU' if gpus > 1 else 'single GPU',
+        'scenes': gpus,
+        'parallelism': ('one mosaic of %d scenes, tiles dealt over %d GPUs in row-major chunks, overlap '
+            'strips over NCCL, ids global' % (gpus, gpus)) if gpus > 1 else 'single GPU',
         'l2_policy': 'inputs larger than L2 (964 MB raster, 482 MB mosaic per scene)'}
 
 
 # ---------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
+SCENE_GRID = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}   # scenes (rows, cols) of the mosaic per N
+
+
 def run_ours(args, wl):
     import torch
-    from pyshepseg_b200 import _lib, shepseg, tiling, rasterfile, timinghooks
+    from pyshepseg_b200 import _lib, shepseg, tiling, rasterfile, timinghooks, distributed
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -267,10 +276,26 @@ def run_ours(args, wl):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
-    # ---- set-up (untimed): scene in pinned host memory, centres from rank 0 over NCCL ----
-    (nB, nR, nC) = (wl['bands'], wl['rows'], wl['cols'])
-    pinnedImg = _lib.PinnedArray((nB, nR, nC), numpy.uint16)
-    img = make_scene(wl, seed=1 + rank, out=pinnedImg.array)
+    # ---- set-up (untimed): the raster in pinned host memory, centres from rank 0 over NCCL ----
+    # N = 1: the scene.  N > 1: ONE mosaic of N scenes (weak scaling), its tiles dealt over the
+    # ranks in contiguous row-major chunks; a rank holds the row band its tiles cover.
+    nB = wl['bands']
+    (gr, gc) = SCENE_GRID.get(world, (1, world))
+    (nR, nC) = (wl['rows'] * gr, wl['cols'] * gc)
+    tileInfo = tiling.getTilesForFile((nC, nR), wl['tileSize'], wl['overlapSize'])
+    comm = None
+    (y0, y1) = (0, nR)
+    if world > 1:
+        comm = distributed.TorchComm(torch.device('cuda', local))
+        owner = distributed.partitionTiles(tileInfo, world)
+        mineT = [tileInfo.tiles[cr] for cr in tileInfo.tiles if owner[cr] == rank]
+        (y0, y1) = (min(t[1] for t in mineT), max(t[1] + t[3] for t in mineT))
+    bandRows = y1 - y0
+    pinnedImg = _lib.PinnedArray((nB, bandRows, nC), numpy.uint16)
+    if world == 1:
+        img = make_scene(wl, seed=1, out=pinnedImg.array)
+    else:
+        img = synth.synth_window(nR, nC, nB, 1, y0, 0, bandRows, nC, out=pinnedImg.array)
     if rank == 0:
         centres = scene_centres(wl, img)
     else:
@@ -283,22 +308,21 @@ def run_ours(args, wl):
     km = KM(centres)
     msd = shepseg.autoMaxSpectralDiff(km, wl['maxSpectralDiff'], 50)
     thr = shepseg.spectralThreshold(msd)
-    tileInfo = tiling.getTilesForFile((nC, nR), wl['tileSize'], wl['overlapSize'])
-    pinnedOut = _lib.PinnedArray((nR, nC), numpy.uint32)
+    pinnedOut = _lib.PinnedArray((bandRows, nC), numpy.uint32)
 
     state = tiling.gpuState(local)
     ctx0 = state.slot(0).ctx
     devImg = ctx0.dev_alloc(img.nbytes)
     ctx0.call('ssg_memcpy_h2d', devImg, _lib.ptr(img), img.nbytes)
     ctx0.synchronize()
-    devMosaic = ctx0.dev_alloc(nR * nC * 4)
+    devMosaic = ctx0.dev_alloc(bandRows * nC * 4)
 
     def step_resident(profile=False):
         cfg = tiling.SegmentationConcurrencyConfig(devices=[local])
-        seg = tiling.TiledSegmenter(tiling.DeviceRaster(devImg, nB, nR, nC, numpy.uint16), range(1, nB + 1),
-            tileInfo, wl['overlapSize'], centres, None, wl['fourConnected'], wl['minSegmentSize'], thr,
-            False, cfg, timinghooks.Timers(), profile=profile)
-        (maxSegId, hist) = seg.run(tiling.DeviceMosaicSink(devMosaic, nC, nR))
+        seg = tiling.TiledSegmenter(tiling.DeviceRaster(devImg, nB, bandRows, nC, numpy.uint16, yoff=y0),
+            range(1, nB + 1), tileInfo, wl['overlapSize'], centres, None, wl['fourConnected'],
+            wl['minSegmentSize'], thr, False, cfg, timinghooks.Timers(), profile=profile)
+        (maxSegId, hist) = seg.run(tiling.DeviceMosaicSink(devMosaic, nC, bandRows, yoff=y0), comm)
         return (seg, maxSegId)
 
     def step_e2e():
@@ -306,23 +330,20 @@ def run_ours(args, wl):
             devices=[local], tileCompletionTimeout=600)
         sink = rasterfile.MemorySink.__new__(rasterfile.MemorySink)
         sink.array = pinnedOut.array
+        sink.yoff = y0
         sink.metadata = {}
         sink.nodata = None
         sink.hist = None
-        seg = tiling.TiledSegmenter(rasterfile.MemoryRaster(img), range(1, nB + 1), tileInfo,
+        src = rasterfile.MemoryRaster(img)
+        src.yoff = y0
+        seg = tiling.TiledSegmenter(src, range(1, nB + 1), tileInfo,
             wl['overlapSize'], centres, None, wl['fourConnected'], wl['minSegmentSize'], thr, False, cfg,
             timinghooks.Timers())
-        (maxSegId, hist) = seg.run(sink)
+        (maxSegId, hist) = seg.run(sink, comm)
         return (seg, maxSegId)
 
     def exchange_ids(maxSegId):
-        """per-scene id base = exclusive scan of the scenes' segment counts (NCCL all-gather)"""
-        if dist is None:
-            return 0
-        mine = torch.tensor([maxSegId], dtype=torch.int64, device='cuda')
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        return int(sum(int(v.item()) for v in allv[:rank]))
+        return 0      # (ids are global already: the sharded stitch numbers the mosaic as a whole)
 
     def barrier():
         if dist is not None:
@@ -376,22 +397,33 @@ def run_ours(args, wl):
     (msE2E, lastE2E) = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    pixelsPerStep = nR * nC * world
+    pixelsPerStep = nR * nC      # unique pixels of the mosaic (all ranks together)
     value = pixelsPerStep * args.steps / (msResident / 1e3) / 1e6
     e2eValue = pixelsPerStep * args.steps / (msE2E / 1e3) / 1e6
     segE2E = lastE2E[0]
+    (h2dBytes, d2hBytes) = (int(segE2E.h2dBytes), int(segE2E.d2hBytes))
+    if dist is not None:       # bytes of all ranks
+        t = torch.tensor([h2dBytes, d2hBytes], dtype=torch.int64, device='cuda')
+        dist.all_reduce(t)
+        (h2dBytes, d2hBytes) = (int(t[0].item()), int(t[1].item()))
 
     # the e2e mosaic must be the resident mosaic (same labels, one went over PCIe)
+    midRow = bandRows // 2
     check = numpy.empty((64, nC), dtype=numpy.uint32)
-    ctx0.call('ssg_memcpy_d2h', _lib.ptr(check), devMosaic + (nR // 2) * nC * 4, check.nbytes)
-    sameMosaic = bool(numpy.array_equal(check, pinnedOut.array[nR // 2:nR // 2 + 64]))
+    ctx0.call('ssg_memcpy_d2h', _lib.ptr(check), devMosaic + midRow * nC * 4, check.nbytes)
+    sameMosaic = bool(numpy.array_equal(check, pinnedOut.array[midRow:midRow + 64]))
+    if dist is not None:
+        t = torch.tensor([int(sameMosaic)], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        sameMosaic = bool(t.item())
 
     if rank == 0:
         (peak, peakKind) = measured_peaks()
         # roofline of the dominant kernel, from the events recorded around every launch
         dom = max(kernelAgg.items(), key=lambda kv: kv[1][1]) if kernelAgg else (None, [0, 0.0])
         (domName, (domCount, domMs)) = dom
-        tilePixels = sum(t[2] * t[3] for t in tileInfo.tiles.values())
+        tilePixels = sum(t[2] * t[3] for (cr, t) in tileInfo.tiles.items()
+            if world == 1 or owner[cr] == rank)     # the kernel times below are rank 0's
         bpp = algorithmic_bytes_per_pixel(domName, nB)
         roof = {'bound': 'hbm', 'kernel': domName, 'achieved': None, 'peak': peak, 'unit': 'GB/s',
             'frac': None, 'traffic': None, 'peak_source': peakKind}
@@ -428,9 +460,9 @@ def run_ours(args, wl):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': msResident / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16', 'data': 'synthetic',
-            'config': workload_config(wl, args.gpus),
+            'config': workload_config(wl, args.gpus, (nR, nC), tileInfo),
             'e2e': {'value': e2eValue, 'unit': UNIT, 'ms_per_step': msE2E / args.steps,
-                'h2d_bytes_per_step': int(segE2E.h2dBytes), 'd2h_bytes_per_step': int(segE2E.d2hBytes),
+                'h2d_bytes_per_step': h2dBytes, 'd2h_bytes_per_step': d2hBytes,
                 'workers': E2E_WORKERS, 'same_labels_as_resident': sameMosaic},
             'gpu_launches': int(launchesResident),
             'roofline': roof, 'roofline_other': extra, 'kernels': kernels,

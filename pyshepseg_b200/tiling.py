@@ -716,24 +716,38 @@ class TiledSegmenter(object):
         workers = []
         ov = self.overlapSize
         cudaDev = torch.device('cuda', self.device)
+        # strips travel device to device (NCCL) unless the communicator is a host one (gloo)
+        onDevice = getattr(comm, 'device', None) is not None and comm.device.type == 'cuda'
+        stripDev = cudaDev if onDevice else torch.device('cpu')
         seg = self
+        keep = []     # device copies of strips received through the host
 
         class Ops(object):
             def sendStrip(self, cr, which):
                 t = seg.tiles[cr]
                 if which == 'bottom':
-                    out = torch.empty((ov, t.xsize), dtype=torch.int32, device=cudaDev)
-                    main.ctx.call('ssg_memcpy_d2d', out.data_ptr(), t.buf[1] + (t.ysize - ov) * t.xsize * 4,
-                        ov * t.xsize * 4)
+                    out = torch.empty((ov, t.xsize), dtype=torch.int32, device=stripDev)
+                    (src, spitch, rows) = (t.buf[1] + (t.ysize - ov) * t.xsize * 4, t.xsize * 4, ov)
+                    width = t.xsize * 4
                 else:
-                    out = torch.empty((t.ysize, ov), dtype=torch.int32, device=cudaDev)
-                    main.ctx.call('ssg_memcpy2d_d2d', out.data_ptr(), ov * 4, t.buf[1] + (t.xsize - ov) * 4,
-                        t.xsize * 4, ov * 4, t.ysize)
+                    out = torch.empty((t.ysize, ov), dtype=torch.int32, device=stripDev)
+                    (src, spitch, rows) = (t.buf[1] + (t.xsize - ov) * 4, t.xsize * 4, t.ysize)
+                    width = ov * 4
+                main.ctx.call('ssg_memcpy2d_d2d' if onDevice else 'ssg_memcpy2d_d2h', out.data_ptr(), width,
+                    src, spitch, width, rows)
                 main.ctx.synchronize()
                 return out
 
             def recvStrip(self, cr, which, shape):
-                return torch.empty(shape, dtype=torch.int32, device=cudaDev)
+                return torch.empty(shape, dtype=torch.int32, device=stripDev)
+
+            def _devStrip(self, t):
+                if t.device.type == 'cuda':
+                    return t
+                d = t.to(cudaDev)
+                torch.cuda.synchronize(cudaDev)
+                keep.append(d)
+                return d
 
             def tables(self, cr, top, left):
                 t = seg.tiles[cr]
@@ -743,12 +757,14 @@ class TiledSegmenter(object):
                         up = seg.tiles[(t.col, t.row - 1)]
                         (topB, topStride) = (up.buf[1] + (up.ysize - ov) * up.xsize * 4, up.xsize)
                     else:
+                        top = self._devStrip(top)
                         (topB, topStride) = (top.data_ptr(), top.shape[1])
                 if left is not None:
                     if isinstance(left, str):
                         lf = seg.tiles[(t.col - 1, t.row)]
                         (leftB, leftStride) = (lf.buf[1] + (lf.xsize - ov) * 4, lf.xsize)
                     else:
+                        left = self._devStrip(left)
                         (leftB, leftStride) = (left.data_ptr(), left.shape[1])
                 return seg.tileTables(main, t, topB, topStride, leftB, leftStride)
 

@@ -1,0 +1,70 @@
+"""
+The sharded tiled path on the GPU: two ranks (gloo process group, both on cuda:0, overlap strips
+staged through the host) segment the tiles of one mosaic between them with the CUDA kernels and
+stitch them with pyshepseg_b200.distributed.  The windows of both ranks together must be the
+mosaic the unmodified reference wrote (tests/golden/tiled_*.npz), with its maxSegId and histogram.
+On a multi-GPU box bench.py --gpus N drives the same code with NCCL and device-to-device strips.
+"""
+import socket
+
+import numpy
+import pytest
+
+import goldenutil
+
+pytestmark = pytest.mark.gpu
+
+
+def _rank_main(rank, world, port, name, resq):
+    import torch.distributed as dist
+    from pyshepseg_b200 import tiling, distributed, rasterfile, shepseg, timinghooks
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    try:
+        c = goldenutil.load(name)
+        m = c['meta']
+        img = c['img']
+        km = goldenutil.Centres(c['centres'])
+        (nB, nR, nC) = img.shape
+        ti = tiling.getTilesForFile((nC, nR), m['tileSize'], m['overlapSize'])
+        msd = shepseg.autoMaxSpectralDiff(km, 'auto', m.get('spectDistPcntile', 50))
+        cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS if rank else tiling.CONC_NONE,
+            numWorkers=2 if rank else 0)
+        seg = tiling.TiledSegmenter(rasterfile.MemoryRaster(img, nodata=m['imgNullVal']), range(1, nB + 1), ti,
+            m['overlapSize'], shepseg._centres(km), m['imgNullVal'], m['fourConnected'], m['minSegmentSize'],
+            shepseg.spectralThreshold(msd), m['simpleTileRecode'], cfg, timinghooks.Timers())
+        sink = rasterfile.MemorySink(nC, nR)
+        comm = distributed.TorchComm()
+        (maxSegId, hist) = seg.run(sink, comm)
+        total = comm.allreduceSum(sink.array.astype(numpy.int64))     # windows are disjoint
+        if rank == 0:
+            resq.put((maxSegId, total.astype(numpy.uint32), hist, seg.usedFallback, seg.launches))
+    finally:
+        dist.destroy_process_group()
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize('name', ['tiled_700x900', 'tiled_null_4x4', 'tiled_640_5x5_8conn', 'tiled_simple_recode'])
+def test_two_ranks_equal_reference_mosaic(name):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    resq = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, name, resq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (maxSegId, mosaic, hist, usedFallback, launches) = resq.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    c = goldenutil.load(name)
+    assert launches > 0
+    assert int(maxSegId) == c['meta']['maxSegId']
+    assert numpy.array_equal(mosaic, c['mosaic'])
+    assert numpy.array_equal(numpy.asarray(hist), c['hist'])
