@@ -94,51 +94,50 @@ class TileTable(object):
                 self.pairCounts.astype(numpy.int64))
         return self._split
 
-    def pack(self):
-        buf = io.BytesIO()
-        buf.write(numpy.array([self.maxId, self.countNew, len(self.rank), len(self.pairKeys)],
-            dtype=numpy.int64).tobytes())
-        for a in (self.pairKeys, self.rank, self.pairCounts, self.flags):   # widest first: aligned
-            buf.write(a.tobytes())
-        return buf.getvalue()
-
-    @staticmethod
-    def unpack(b):
-        hdr = numpy.frombuffer(b, dtype=numpy.int64, count=4)
-        (maxId, countNew, n, m) = (int(v) for v in hdr)
-        o = 32
-        pairKeys = numpy.frombuffer(b, dtype=numpy.uint64, count=m, offset=o)
-        o += 8 * m
-        rank = numpy.frombuffer(b, dtype=numpy.uint32, count=n, offset=o)
-        o += 4 * n
-        pairCounts = numpy.frombuffer(b, dtype=numpy.uint32, count=m, offset=o)
-        o += 4 * m
-        flags = numpy.frombuffer(b, dtype=numpy.uint8, count=n, offset=o)
-        return TileTable(maxId, countNew, rank, flags, pairKeys, pairCounts)
-
 
 def packTables(tables):
-    """{tile: TileTable} -> bytes (for an all-gather of byte buffers)."""
-    buf = io.BytesIO()
-    buf.write(numpy.array([len(tables)], dtype=numpy.int64).tobytes())
-    for (cr, tb) in sorted(tables.items()):
-        body = tb.pack()
-        pad = (-len(body)) % 8
-        buf.write(numpy.array([cr[0], cr[1], len(body) + pad], dtype=numpy.int64).tobytes())
-        buf.write(body)
-        buf.write(b'\0' * pad)
-    return buf.getvalue()
+    """{tile: TileTable} -> one uint8 array (for an all-gather of byte buffers)."""
+    items = sorted(tables.items())
+    total = 8
+    for (cr, tb) in items:
+        total += 24 + 32 + 8 * len(tb.pairKeys) + 4 * len(tb.rank) + 4 * len(tb.pairCounts) + len(tb.flags)
+        total += (-total) % 8
+    out = numpy.zeros(total, dtype=numpy.uint8)
+    out[:8].view(numpy.int64)[0] = len(items)
+    o = 8
+    for (cr, tb) in items:
+        body = 32 + 8 * len(tb.pairKeys) + 4 * len(tb.rank) + 4 * len(tb.pairCounts) + len(tb.flags)
+        size = body + ((-(o + 24 + body)) % 8)
+        out[o:o + 24].view(numpy.int64)[:] = (cr[0], cr[1], size)
+        o += 24
+        out[o:o + 32].view(numpy.int64)[:] = (tb.maxId, tb.countNew, len(tb.rank), len(tb.pairKeys))
+        q = o + 32
+        for a in (tb.pairKeys, tb.rank, tb.pairCounts, tb.flags):      # widest first: aligned
+            nb = a.nbytes
+            out[q:q + nb] = a.view(numpy.uint8)
+            q += nb
+        o += size
+    return out
 
 
 def unpackTables(b):
-    b = bytes(b)
-    n = int(numpy.frombuffer(b, dtype=numpy.int64, count=1)[0])
+    b = numpy.frombuffer(b, dtype=numpy.uint8) if not isinstance(b, numpy.ndarray) else b
+    n = int(b[:8].view(numpy.int64)[0])
     o = 8
     out = {}
     for _ in range(n):
-        (c, r, size) = (int(v) for v in numpy.frombuffer(b, dtype=numpy.int64, count=3, offset=o))
+        (c, r, size) = (int(v) for v in b[o:o + 24].view(numpy.int64))
         o += 24
-        out[(c, r)] = TileTable.unpack(b[o:o + size])
+        (maxId, countNew, nSeg, nPairs) = (int(v) for v in b[o:o + 32].view(numpy.int64))
+        q = o + 32
+        pairKeys = b[q:q + 8 * nPairs].view(numpy.uint64)
+        q += 8 * nPairs
+        rank = b[q:q + 4 * nSeg].view(numpy.uint32)
+        q += 4 * nSeg
+        pairCounts = b[q:q + 4 * nPairs].view(numpy.uint32)
+        q += 4 * nPairs
+        flags = b[q:q + nSeg]
+        out[(c, r)] = TileTable(maxId, countNew, rank, flags, pairKeys, pairCounts)
         o += size
     return out
 
@@ -165,6 +164,7 @@ class LazyResolver(object):
         self.simple = simple
         self.luts = {}
         self.missing = set()    # tiles a look-up reached without their table being here
+        self.misses = 0         # how often that happened (a tile can be reached many times)
 
     def _lutOf(self, cr):
         if cr not in self.luts:
@@ -178,11 +178,16 @@ class LazyResolver(object):
         self.missing = set()
 
     def finalIds(self, cr, labels):
-        """final ids of the given local labels of tile cr (int64 array, any shape)"""
+        """final ids of the given local labels of tile cr (int64 array).  Entries whose value
+        hangs on a table that is not here stay unknown (and come back as 0): the tile is noted in
+        self.missing, to be fetched before the next call."""
         from .tiling import _modeByKey
         lut = self._lutOf(cr)
         labels = numpy.asarray(labels, dtype=numpy.int64)
-        need = numpy.unique(labels[lut[labels] == self.UNKNOWN])
+        wantMask = numpy.zeros(len(lut), dtype=bool)
+        wantMask[labels] = True
+        wantMask &= (lut == self.UNKNOWN)
+        need = numpy.flatnonzero(wantMask)
         if len(need) > 0:
             tb = self.tables[cr]
             off = self.offsets[cr]
@@ -194,28 +199,45 @@ class LazyResolver(object):
                 numbered = (fl & _lib.SEG_NUMBERED) != 0
                 vals[numbered] = tb.rank[need[numbered]] + numpy.uint32(off)
                 lut[need] = vals
-                keyed = need[(fl & KEY_FLAGS) != 0]
-                if len(keyed) > 0 and len(tb.pairKeys) > 0:
+                # a crossing segment: the vote of the left overlap if it crosses that one (the left
+                # recode is applied after the top one and overrides it, tiling.py:1107-1121),
+                # otherwise the vote of the top overlap
+                if len(tb.pairKeys) > 0:
                     (isLeft, segs, nbr, counts) = tb.pairs()
-                    wanted = numpy.zeros(tb.maxId + 1, dtype=bool)
-                    wanted[keyed] = True
-                    mine = wanted[segs]
-                    for (sel, nb) in ((mine & ~isLeft, (cr[0], cr[1] - 1)), (mine & isLeft, (cr[0] - 1, cr[1]))):
+                    byLeft = (fl & _lib.SEG_KEYLEFT) != 0
+                    byTop = ((fl & _lib.SEG_KEYTOP) != 0) & ~byLeft
+                    for (which, pairSide, nb) in ((byTop, ~isLeft, (cr[0], cr[1] - 1)),
+                            (byLeft, isLeft, (cr[0] - 1, cr[1]))):
+                        if not which.any():
+                            continue
+                        wanted = numpy.zeros(tb.maxId + 1, dtype=bool)
+                        wanted[need[which]] = True
+                        sel = pairSide & wanted[segs]
                         if not sel.any():
                             continue
-                        try:
-                            mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
-                        except MissingTable as e:
-                            # noted; the caller fetches the table and resolves again
-                            self.missing.add(e.args[0])
+                        if nb not in self.tables:
+                            # noted; the entries stay open until the table has been fetched
+                            self.missing.add(nb)
+                            self.misses += 1
+                            lut[need[which]] = self.UNKNOWN
+                            continue
+                        before = self.misses
+                        mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
+                        if self.misses > before:
+                            # the neighbour's own answer is still open somewhere below
+                            lut[need[which]] = self.UNKNOWN
                             continue
                         (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
                         lut[k] = mode.astype(numpy.uint32)
-        return lut[labels]
+        out = lut[labels]
+        return numpy.where(out == self.UNKNOWN, 0, out).astype(numpy.uint32)
 
     def fullLut(self, cr):
         n = self.tables[cr].maxId + 1
         return self.finalIds(cr, numpy.arange(n, dtype=numpy.int64))
+
+    def complete(self, cr):
+        return cr in self.luts and not (self.luts[cr] == self.UNKNOWN).any()
 
 
 def sequentialResolve(order, tables, simple=False):
@@ -248,7 +270,8 @@ class LocalComm(object):
         return [list(values)]
 
     def allgatherBytes(self, b):
-        return [bytes(b)]
+        """uint8 array (or bytes) from every rank -> list of uint8 arrays"""
+        return [numpy.frombuffer(b, dtype=numpy.uint8) if not isinstance(b, numpy.ndarray) else b]
 
     def exchange(self, sends, recvs):
         """sends: [(dstRank, tensor)], recvs: [(srcRank, tensor)] in matching order per rank pair"""
@@ -286,14 +309,16 @@ class TorchComm(object):
         return [o.cpu().numpy()[:sizes[i]].tolist() for (i, o) in enumerate(out)]
 
     def allgatherBytes(self, b):
+        if not isinstance(b, numpy.ndarray):
+            b = numpy.frombuffer(b, dtype=numpy.uint8)
         sizes = [s[0] for s in self.allgatherInts([len(b)])]
         m = max(max(sizes), 1)
         mine = numpy.zeros(m, dtype=numpy.uint8)
-        mine[:len(b)] = numpy.frombuffer(b, dtype=numpy.uint8)
+        mine[:len(b)] = b
         mine = self._t(mine)
         out = [self.torch.zeros_like(mine) for _ in range(self.world)]
         self.dist.all_gather(out, mine)
-        return [o.cpu().numpy()[:sizes[i]].tobytes() for (i, o) in enumerate(out)]
+        return [o.cpu().numpy()[:sizes[i]] for (i, o) in enumerate(out)]
 
     def exchange(self, sends, recvs):
         ops = []
@@ -327,7 +352,8 @@ class ShardedStitch(object):
                                           the tensor received for it
       ops.apply(cr, lut, table)           write lut[tile] over the trimmed window of own tile cr
     """
-    def __init__(self, tileInfo, overlapSize, simple, comm):
+    def __init__(self, tileInfo, overlapSize, simple, comm, timings=None):
+        self.timings = timings
         self.tileInfo = tileInfo
         self.overlap = int(overlapSize)
         self.simple = simple
@@ -366,8 +392,26 @@ class ShardedStitch(object):
                     recvs.append((self.owner[nb], nb, which, shape))
         return (sends, recvs)
 
+    def _timed(self, name):
+        import contextlib
+        return self.timings.interval(name) if self.timings is not None else contextlib.nullcontext()
+
     def run(self, ops):
         """returns (maxSegId, offsets of all tiles, luts of own tiles)"""
+        with self._timed('stitch_strips'):
+            received = self._exchangeStrips(ops)
+        with self._timed('stitch_owntables'):
+            tables = self._ownTables(ops, received)
+        with self._timed('stitch_offsets'):
+            (steps, offsets, maxSegId) = self._offsets(tables)
+        with self._timed('stitch_resolve'):
+            (luts, offsets, maxSegId) = self._resolve(tables, steps, offsets, maxSegId)
+        with self._timed('stitch_apply'):
+            for cr in self.mine:
+                ops.apply(cr, luts[cr], tables[cr])
+        return (maxSegId, offsets, luts)
+
+    def _exchangeStrips(self, ops):
         comm = self.comm
         # 1. strips of remote neighbours
         (sends, recvs) = self.stripPlan()
@@ -379,7 +423,10 @@ class ShardedStitch(object):
             received[(cr, which)] = t
             recvList.append((peer, t))
         comm.exchange(sendList, recvList)
+        return received
 
+    def _ownTables(self, ops, received):
+        comm = self.comm
         # 2. tables of own tiles
         tables = {}
         for cr in self.mine:
@@ -391,7 +438,10 @@ class ShardedStitch(object):
                 if left is not None:
                     lf = 'local' if self.owner[left] == comm.rank else received[(left, 'right')]
             tables[cr] = ops.tables(cr, top, lf)
+        return tables
 
+    def _offsets(self, tables):
+        comm = self.comm
         # 3. offsets.  The reference moves the running maximum on tile after tile:
         # maxSegId = max(maxSegId, trimmed.max()) (tiling.py:1042-1043).  Inside the trimmed
         # window a tile has its own numbered segments (offset + rank) and segments recoded to ids
@@ -415,7 +465,10 @@ class ShardedStitch(object):
             offsets[cr] = offset
             offset += steps[cr]
         maxSegId = offset
+        return (steps, offsets, maxSegId)
 
+    def _resolve(self, tables, steps, offsets, maxSegId):
+        comm = self.comm
         # 4. final ids of own tiles.  Tables of the tiles that a tile on another rank looks into
         # are fetched on request: first the direct neighbours across a rank boundary, then
         # whatever the look-ups ask for beyond them (a crossing segment's id can be inherited
@@ -437,11 +490,12 @@ class ShardedStitch(object):
                 give = dict((cr, tables[cr]) for cr in asked if cr in tables)
                 for b in comm.allgatherBytes(packTables(give)):
                     for (cr, tb) in unpackTables(b).items():
-                        known.setdefault(cr, tb)
+                        if cr not in known:
+                            known[cr] = tb
             elif luts:
                 break
-            resolver.reset()
-            for cr in self.mine:
+            resolver.missing = set()
+            for cr in self.mine:          # (entries settled in an earlier round are kept)
                 luts[cr] = resolver.fullLut(cr)
             want = set(resolver.missing)
         else:
@@ -463,7 +517,4 @@ class ShardedStitch(object):
             (allLuts, offsets, maxSegId) = sequentialResolve(self.order, known, self.simple)
             luts = dict((cr, allLuts[cr]) for cr in self.mine)
 
-        # 5. apply
-        for cr in self.mine:
-            ops.apply(cr, luts[cr], tables[cr])
-        return (maxSegId, offsets, luts)
+        return (luts, offsets, maxSegId)

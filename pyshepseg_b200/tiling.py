@@ -710,7 +710,7 @@ class TiledSegmenter(object):
         pool = state.pool
         main = state.slot(0)
         hist = state.hist
-        stitch = distributed.ShardedStitch(self.tileInfo, self.overlapSize, self.simple, comm)
+        stitch = distributed.ShardedStitch(self.tileInfo, self.overlapSize, self.simple, comm, self.timings)
         mine = stitch.mine
         numWorkers = cfg.numWorkers if cfg.concurrencyType == CONC_THREADS else 0
         workers = []

@@ -191,5 +191,6 @@ def test_table_pack_roundtrip():
     assert sorted(back) == sorted(tabs)
     for cr in tabs:
         for f in ('rank', 'flags', 'pairKeys', 'pairCounts'):
+            assert getattr(back[cr], f).dtype == getattr(tabs[cr], f).dtype
             assert numpy.array_equal(getattr(back[cr], f), getattr(tabs[cr], f))
         assert (back[cr].maxId, back[cr].countNew) == (tabs[cr].maxId, tabs[cr].countNew)
