@@ -167,10 +167,21 @@ class LazyResolver(object):
         self.misses = 0         # how often that happened (a tile can be reached many times)
 
     def _lutOf(self, cr):
+        """the tile's lut with everything that needs no neighbour filled in (one vectorised pass);
+        crossing segments start out unknown"""
         if cr not in self.luts:
             if cr not in self.tables:
                 raise MissingTable(cr)
-            self.luts[cr] = numpy.full(self.tables[cr].maxId + 1, self.UNKNOWN, dtype=numpy.uint32)
+            tb = self.tables[cr]
+            off = numpy.uint32(self.offsets[cr])
+            if self.simple:
+                lut = numpy.arange(tb.maxId + 1, dtype=numpy.uint32) + off
+                lut[0] = 0
+            else:
+                lut = numpy.where((tb.flags & _lib.SEG_NUMBERED) != 0, tb.rank + off, numpy.uint32(0))
+                lut = lut.astype(numpy.uint32)
+                lut[(tb.flags & KEY_FLAGS) != 0] = self.UNKNOWN
+            self.luts[cr] = lut
         return self.luts[cr]
 
     def reset(self):
@@ -181,63 +192,50 @@ class LazyResolver(object):
         """final ids of the given local labels of tile cr (int64 array).  Entries whose value
         hangs on a table that is not here stay unknown (and come back as 0): the tile is noted in
         self.missing, to be fetched before the next call."""
-        from .tiling import _modeByKey
         lut = self._lutOf(cr)
         labels = numpy.asarray(labels, dtype=numpy.int64)
-        wantMask = numpy.zeros(len(lut), dtype=bool)
-        wantMask[labels] = True
-        wantMask &= (lut == self.UNKNOWN)
-        need = numpy.flatnonzero(wantMask)
-        if len(need) > 0:
-            tb = self.tables[cr]
-            off = self.offsets[cr]
-            if self.simple:
-                lut[need] = numpy.where(need > 0, need + off, 0).astype(numpy.uint32)
-            else:
-                fl = tb.flags[need]
-                vals = numpy.zeros(len(need), dtype=numpy.uint32)
-                numbered = (fl & _lib.SEG_NUMBERED) != 0
-                vals[numbered] = tb.rank[need[numbered]] + numpy.uint32(off)
-                lut[need] = vals
-                # a crossing segment: the vote of the left overlap if it crosses that one (the left
-                # recode is applied after the top one and overrides it, tiling.py:1107-1121),
-                # otherwise the vote of the top overlap
-                if len(tb.pairKeys) > 0:
-                    (isLeft, segs, nbr, counts) = tb.pairs()
-                    byLeft = (fl & _lib.SEG_KEYLEFT) != 0
-                    byTop = ((fl & _lib.SEG_KEYTOP) != 0) & ~byLeft
-                    for (which, pairSide, nb) in ((byTop, ~isLeft, (cr[0], cr[1] - 1)),
-                            (byLeft, isLeft, (cr[0] - 1, cr[1]))):
-                        if not which.any():
-                            continue
-                        wanted = numpy.zeros(tb.maxId + 1, dtype=bool)
-                        wanted[need[which]] = True
-                        sel = pairSide & wanted[segs]
-                        if not sel.any():
-                            continue
-                        if nb not in self.tables:
-                            # noted; the entries stay open until the table has been fetched
-                            self.missing.add(nb)
-                            self.misses += 1
-                            lut[need[which]] = self.UNKNOWN
-                            continue
-                        before = self.misses
-                        mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
-                        if self.misses > before:
-                            # the neighbour's own answer is still open somewhere below
-                            lut[need[which]] = self.UNKNOWN
-                            continue
-                        (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
-                        lut[k] = mode.astype(numpy.uint32)
         out = lut[labels]
+        unknown = out == self.UNKNOWN
+        if unknown.any():
+            self._resolveCrossing(cr, lut, labels[unknown])
+            out = lut[labels]
         return numpy.where(out == self.UNKNOWN, 0, out).astype(numpy.uint32)
 
-    def fullLut(self, cr):
-        n = self.tables[cr].maxId + 1
-        return self.finalIds(cr, numpy.arange(n, dtype=numpy.int64))
+    def _resolveCrossing(self, cr, lut, labels):
+        """A crossing segment takes the vote of the left overlap if it crosses that one (the left
+        recode is applied after the top one and overrides it, tiling.py:1107-1121), otherwise the
+        vote of the top overlap."""
+        from .tiling import _modeByKey
+        tb = self.tables[cr]
+        (isLeft, segs, nbr, counts) = tb.pairs()
+        wanted = numpy.zeros(tb.maxId + 1, dtype=bool)
+        wanted[labels] = True
+        keyLeft = (tb.flags & _lib.SEG_KEYLEFT) != 0
+        for (which, pairSide, nb) in ((wanted & ~keyLeft, ~isLeft, (cr[0], cr[1] - 1)),
+                (wanted & keyLeft, isLeft, (cr[0] - 1, cr[1]))):
+            sel = pairSide & which[segs]
+            if not sel.any():
+                lut[which] = 0
+                continue
+            if nb not in self.tables:
+                # noted; the entries stay open until the table has been fetched
+                self.missing.add(nb)
+                self.misses += 1
+                continue
+            before = self.misses
+            mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
+            if self.misses > before:
+                continue          # the neighbour's own answer is still open somewhere below
+            lut[which] = 0
+            (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
+            lut[k] = mode.astype(numpy.uint32)
 
-    def complete(self, cr):
-        return cr in self.luts and not (self.luts[cr] == self.UNKNOWN).any()
+    def fullLut(self, cr):
+        lut = self._lutOf(cr)
+        unknown = numpy.flatnonzero(lut == self.UNKNOWN)
+        if len(unknown) > 0:
+            self._resolveCrossing(cr, lut, unknown)
+        return numpy.where(lut == self.UNKNOWN, 0, lut).astype(numpy.uint32)
 
 
 def sequentialResolve(order, tables, simple=False):
