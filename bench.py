@@ -50,7 +50,9 @@ WORKLOAD = {
 }
 METRIC = 'Mpixels/sec full segmentation (assign+clump+eliminate+stitch), tiled 10980x10980x4 uint16'
 UNIT = 'Mpixel/s'
-E2E_WORKERS = int(os.environ.get('BENCH_E2E_WORKERS', '2'))   # segmentation workers of the host-to-host run
+E2E_WORKERS = int(os.environ.get('BENCH_E2E_WORKERS', '3'))   # segmentation workers of the host-to-host run
+SCENE_GRID = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}   # scenes (rows, cols) of the mosaic per N
+RESIDENT_WORKERS = int(os.environ.get('BENCH_RESIDENT_WORKERS', '2'))   # 0: segment and stitch in one thread
 
 # algorithmic bytes per pixel of the kernels:
 # what one launch must move at the very least, per pixel it processes
@@ -216,6 +218,9 @@ def run_reference(args, wl):
     tile = 2048 if args.quick else 4096
     img = make_scene(wl, seed=1)
     centres = scene_centres(wl, img)
+    from pyshepseg_b200 import tiling
+    (gr, gc) = SCENE_GRID.get(args.gpus, (1, args.gpus))
+    tileInfo = tiling.getTilesForFile((wl['cols'] * gc, wl['rows'] * gr), wl['tileSize'], wl['overlapSize'])
     for _ in range(args.warmup):
         cpu_reference_sample(wl, img, centres, threads, tile=min(tile, 1024))
     pix = 0
@@ -231,7 +236,7 @@ def run_reference(args, wl):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16',
-        'data': 'synthetic', 'config': workload_config(wl, args.gpus),
+        'data': 'synthetic', 'config': workload_config(wl, args.gpus, None, tileInfo),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -257,9 +262,6 @@ def workload_config(wl, gpus, shape=None, tileInfo=None):
 # ---------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
-SCENE_GRID = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}   # scenes (rows, cols) of the mosaic per N
-
-
 def run_ours(args, wl):
     import torch
     from pyshepseg_b200 import _lib, shepseg, tiling, rasterfile, timinghooks, distributed
@@ -318,7 +320,9 @@ def run_ours(args, wl):
     devMosaic = ctx0.dev_alloc(bandRows * nC * 4)
 
     def step_resident(profile=False):
-        cfg = tiling.SegmentationConcurrencyConfig(devices=[local])
+        cfg = tiling.SegmentationConcurrencyConfig(devices=[local]) if (RESIDENT_WORKERS == 0 or profile) else \
+            tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=RESIDENT_WORKERS,
+                devices=[local], tileCompletionTimeout=600)
         seg = tiling.TiledSegmenter(tiling.DeviceRaster(devImg, nB, bandRows, nC, numpy.uint16, yoff=y0),
             range(1, nB + 1), tileInfo, wl['overlapSize'], centres, None, wl['fourConnected'],
             wl['minSegmentSize'], thr, False, cfg, timinghooks.Timers(), profile=profile)
@@ -392,9 +396,13 @@ def run_ours(args, wl):
             ent[0] += v[0]
             ent[1] += v[1]
         return r
-    (msResident, lastRes) = timed(resident_profiled, args.steps)
+    (msResident, lastRes) = timed(step_resident, args.steps)
     launchesResident = sum(s.ctx.launch_count() for s in state.slots) - launches0
     (msE2E, lastE2E) = timed(step_e2e, args.steps)
+    # per-kernel durations for the roofline: the same steps once more on ONE stream with an event
+    # pair around every launch (with several worker streams an event pair would also span the
+    # other streams' kernels)
+    (msProfiled, lastProf) = timed(resident_profiled, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     pixelsPerStep = nR * nC      # unique pixels of the mosaic (all ranks together)
@@ -437,7 +445,9 @@ def run_ours(args, wl):
             roof['bytes_per_pixel'] = bpp
             roof['avg_launch_ms'] = avgMs
             roof['launches_per_step'] = launchesPerStep
-            roof['share_of_step'] = domMs / msResident
+            roof['share_of_step'] = domMs / msProfiled
+            roof['timed_in'] = ('%d single-stream steps after the timed region, event pair per launch '
+                '(%.1f ms per step)' % (args.steps, msProfiled / args.steps))
         kernels = dict((k, {'launches': v[0], 'ms': round(v[1], 3)}) for (k, v) in sorted(kernelAgg.items(),
             key=lambda kv: -kv[1][1])[:12])
         # secondary rooflines of the two bandwidth kernels the north star names
@@ -468,7 +478,7 @@ def run_ours(args, wl):
             'roofline': roof, 'roofline_other': extra, 'kernels': kernels,
             'cpu_baseline': cpu, 'clocks': clocks,
             'segments_per_scene': int(lastRes[1]),
-            'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastRes[0].stageMs.items()),
+            'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastProf[0].stageMs.items()),
             'host_ms_last_step': {
                 'resident': dict((k, round(v['total'] * 1e3, 2)) for (k, v) in
                     lastRes[0].timings.makeSummaryDict().items()),

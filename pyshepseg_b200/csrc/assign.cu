@@ -7,13 +7,15 @@
 //
 // How it is done here: each thread takes V consecutive pixels of every band plane with one
 // wide load per band (coalesced, 16 B per lane for uint16 at V=8), the centres sit in
-// shared memory (float32 copy for the fast pass, float64 copy for the exact pass) and are
-// read as warp-wide broadcasts.  The fast pass evaluates sum_b (x_b - c_jb)^2 in float32
-// FFMA and tracks the best and second-best value.  Its rounding error is bounded by
-// E(D) = 2^-23 * (Cmax*sqrt(nB)*sqrt(D) + (nB+3)*D); whenever the best/second gap is inside
-// 4*E(D_second) + (float64 margin) the pixel is re-evaluated in float64 with exactly the
-// operation sequence of the oracle (separate multiply and add, no FMA), so the label equals
-// the float64 argmin in every case, ties included.
+// shared memory (float32 copies of -2c and ||c||^2 for the fast pass, float64 copies for the
+// exact pass) and are read as warp-wide broadcasts.  The fast pass evaluates
+// ||c_j||^2 - 2 x.c_j as nB chained FFMAs per centre (half the FP32 work of sum (x-c)^2) and
+// tracks the best and second-best value.  With u = 2^-24 every such value is within
+// E = (nB+1) * 1.01 * u * (max||c||^2 + 2 max|c| sum_b |x_b|) of the real one, so whenever
+// second - best > 2E (+ the float64 margin) the float32 argmin IS the float64 argmin; otherwise
+// the pixel is re-evaluated in float64 with exactly the operation sequence of the oracle
+// (separate multiply and add, no FMA), so the label equals the float64 first-minimum argmin
+// in every case, ties included.
 #include "common.cuh"
 
 template <typename T, int V>
@@ -47,7 +49,7 @@ __device__ __forceinline__ void load_vec(const T *p, float (&x)[V])
 }
 
 struct AssignBounds {
-    float alpha, beta, gamma;
+    float perAbsX, constant;   // tolerance on second - best = perAbsX * sum_b |x_b| + constant
 };
 
 // exact pass for one pixel: same float64 sequence as the oracle / scikit-learn form
@@ -76,12 +78,12 @@ k_assign(const T *__restrict__ img, int64_t N, const double *__restrict__ centre
     extern __shared__ __align__(16) unsigned char smemRaw[];
     double *cd = reinterpret_cast<double *>(smemRaw);          // k*NB
     double *cn = cd + (size_t)k * NB;                          // k
-    float *cf = reinterpret_cast<float *>(cn + k);             // k*NB
+    float *cf = reinterpret_cast<float *>(cn + k);             // k*(NB+1): ||c||^2, then -2c
 
     for (int i = threadIdx.x; i < k * NB; i += blockDim.x) {
         double c = centres[i];
         cd[i] = c;
-        cf[i] = (float)c;
+        cf[(i / NB) * (NB + 1) + 1 + (i % NB)] = (float)(-2.0 * c);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
@@ -89,6 +91,7 @@ k_assign(const T *__restrict__ img, int64_t N, const double *__restrict__ centre
 #pragma unroll
         for (int b = 0; b < NB; b++) s = __dadd_rn(s, __dmul_rn(cd[j * NB + b], cd[j * NB + b]));
         cn[j] = s;
+        cf[j * (NB + 1)] = (float)s;
     }
     __syncthreads();
 
@@ -120,17 +123,14 @@ k_assign(const T *__restrict__ img, int64_t N, const double *__restrict__ centre
         for (int v = 0; v < V; v++) { best[v] = 3.0e38f; second[v] = 3.0e38f; idx[v] = 0; }
 
         for (int j = 0; j < k; j++) {
-            float c[NB];
+            float c[NB + 1];
 #pragma unroll
-            for (int b = 0; b < NB; b++) c[b] = cf[j * NB + b];
+            for (int b = 0; b <= NB; b++) c[b] = cf[j * (NB + 1) + b];
 #pragma unroll
             for (int v = 0; v < V; v++) {
-                float acc = 0.0f;
+                float acc = c[0];
 #pragma unroll
-                for (int b = 0; b < NB; b++) {
-                    float df = x[v][b] - c[b];
-                    acc = fmaf(df, df, acc);
-                }
+                for (int b = 0; b < NB; b++) acc = fmaf(x[v][b], c[b + 1], acc);
                 second[v] = fminf(second[v], fmaxf(acc, best[v]));
                 bool lt = acc < best[v];
                 best[v] = fminf(acc, best[v]);
@@ -142,7 +142,10 @@ k_assign(const T *__restrict__ img, int64_t N, const double *__restrict__ centre
 #pragma unroll
         for (int v = 0; v < V; v++) {
             float gap = second[v] - best[v];
-            float tol = 4.0f * (bnd.alpha * sqrtf(second[v]) + bnd.beta * second[v]) + bnd.gamma;
+            float absSum = 0.0f;
+#pragma unroll
+            for (int b = 0; b < NB; b++) absSum += fabsf(x[v][b]);
+            float tol = fmaf(bnd.perAbsX, absSum, bnd.constant);
             int lab = idx[v];
             if (k > 1 && !(gap > tol)) {
                 float xv[NB];   // copy: keeps x[][] itself in registers
@@ -188,7 +191,7 @@ template <typename T, int NB, int V>
 static int launch_assign(ssg_ctx *ctx, const void *img, int64_t N, const double *centresDev, int k,
                          int hasNull, double nullVal, AssignBounds bnd, int32_t *out)
 {
-    size_t smem = (size_t)k * NB * (sizeof(double) + sizeof(float)) + (size_t)k * sizeof(double);
+    size_t smem = (size_t)k * NB * sizeof(double) + (size_t)k * sizeof(double) + (size_t)k * (NB + 1) * sizeof(float);
     auto kern = k_assign<T, NB, V>;
     if (smem > 48 * 1024)
         SSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -243,14 +246,24 @@ int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t
     SSG_CUDA(ctx, cudaMemcpyAsync(ctx->centres.p, ctx->centresStage.data(), nc * sizeof(double),
                                   cudaMemcpyHostToDevice, ctx->stream));
     const double *centresDev = bufp<double>(ctx->centres);
-    double cmax = 0.0;
-    for (size_t i = 0; i < nc; i++) { double a = fabs(centresHost[i]); if (a > cmax) cmax = a; }
+    double cmax = 0.0, cnmax = 0.0;
+    for (int j = 0; j < k; j++) {
+        double n2 = 0.0;
+        for (int b = 0; b < nBands; b++) {
+            const double a = fabs(centresHost[(size_t)j * nBands + b]);
+            if (a > cmax) cmax = a;
+            n2 += a * a;
+        }
+        if (n2 > cnmax) cnmax = n2;
+    }
     const double xmax = dtype == SSG_U8 ? 255.0 : (dtype == SSG_U16 ? 65535.0 : 32768.0);
-    const double e23 = 1.0 / 8388608.0;
+    const double u = ldexp(1.0, -24);
+    // 2E of the fast pass (see the header) + what float64 itself can be off by in the reference
+    const double e32 = 2.0 * (nBands + 1) * 1.01 * u;
+    const double margin64 = ldexp(1.0, -50) * (nBands + 2) * (cnmax + 2.0 * nBands * xmax * cmax) + 1e-30;
     AssignBounds bnd;
-    bnd.alpha = (float)(e23 * (cmax + xmax * e23) * sqrt((double)nBands) * 1.01);
-    bnd.beta = (float)(e23 * (nBands + 3) * 1.01);
-    bnd.gamma = (float)(ldexp(1.0, -50) * (nBands + 2) * (nBands * cmax * cmax + 2.0 * nBands * xmax * cmax) + 1e-30);
+    bnd.perAbsX = (float)(e32 * 2.0 * cmax * 1.001);
+    bnd.constant = (float)((e32 * cnmax + margin64) * 1.001);
     switch (dtype) {
     case SSG_U8: return dispatch_nb<uint8_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);
     case SSG_U16: return dispatch_nb<uint16_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);

@@ -310,12 +310,9 @@ k_gather_ids(const unsigned *__restrict__ label, int64_t nRows, int64_t nCols, i
                 if (single) sList[base + __popc(m & ((1u << lane_id()) - 1u))] = (unsigned)p;
             }
         }
-        // size histogram: one atomic per distinct id per warp
-        const unsigned active = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned peers = __match_any_sync(active, id);
-            if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&segSize[id], (unsigned)__popc(peers));
-        }
+        // size histogram: one atomic per run of equal ids in the warp
+        const WarpRuns run = warp_runs(id, valid);
+        if (run.head) atomicAdd(&segSize[id], run.len);
     }
     if (!singles) return;
     __syncthreads();
@@ -547,10 +544,8 @@ k_seg_size(const unsigned *__restrict__ seg, int64_t N, unsigned *segSize, int64
     bool valid = p < N;
     unsigned id = valid ? seg[p] : 0;
     if (valid && (int64_t)id >= len) valid = false;
-    unsigned active = __ballot_sync(0xffffffffu, valid);
-    if (!valid) return;
-    unsigned peers = __match_any_sync(active, id);
-    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&segSize[id], (unsigned)__popc(peers));
+    const WarpRuns run = warp_runs(id, valid);
+    if (run.head) atomicAdd(&segSize[id], run.len);
 }
 
 int ssgk_seg_size(ssg_ctx *ctx, const uint32_t *segDev, int64_t N, uint32_t *sizeDev, int64_t len)

@@ -292,14 +292,13 @@ k_band_sums(const T *__restrict__ img, int nB, int64_t N, const unsigned *__rest
     const bool valid = p < N;
     const unsigned s = valid ? seg[p] : 0u;
     const bool use = valid && s != 0;
-    const unsigned active = __ballot_sync(0xffffffffu, use);
-    if (!use) return;
-    const unsigned peers = __match_any_sync(active, s);
-    const bool leader = (int)lane_id() == __ffs(peers) - 1;
+    // one atomic per band per run of equal labels in the warp's 32 consecutive pixels
+    const WarpRuns run = warp_runs(s, use);
     for (int b = 0; b < nB; b++) {
-        int v = (int)img[(size_t)b * N + p];
-        int tot = __reduce_add_sync(peers, v);   // <= 32 * 65535, fits
-        if (leader) atomicAdd(&isum[(size_t)s * nB + b], (unsigned long long)(long long)tot);
+        const int v = use ? (int)img[(size_t)b * N + p] : 0;
+        // 32 x 65535 fits; int16 goes through the unsigned add as two's complement
+        const unsigned tot = run_suffix_add((unsigned)v, run);
+        if (run.head) atomicAdd(&isum[(size_t)s * nB + b], (unsigned long long)(long long)(int)tot);
     }
 }
 

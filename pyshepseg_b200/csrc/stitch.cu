@@ -56,27 +56,28 @@ k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, 
     const bool valid = p < ysize * xsize;
     const unsigned s = valid ? tile[p] : 0u;
     const bool use = valid && s != 0;
-    const unsigned active = __ballot_sync(0xffffffffu, use);
-    if (!use) return;
     const unsigned r = (unsigned)(p / xsize), c = (unsigned)(p % xsize);
-    const unsigned peers = __match_any_sync(active, s);
-    const bool leader = (int)lane_id() == __ffs(peers) - 1;
-    // a warp spans at most two raster rows, so reduce both coordinates over the peers
-    const unsigned rMin = __reduce_min_sync(peers, r), cMin = __reduce_min_sync(peers, c);
+    // runs of equal labels inside one raster row: the head lane knows the run's row and its first
+    // and last column, which is all the extents need -- no reductions.  A table entry is only
+    // touched when the run can improve it (most runs lie below / right of the segment's corner).
+    const WarpRuns run = warp_runs(s, use, c == 0);
+    if (!run.head) return;
+    const unsigned cEnd = c + run.len - 1u;
     const bool inTop = r < topRows, inLeft = c < leftCols;
-    const unsigned tLo = __reduce_min_sync(peers, inTop ? r : SSG_NIL);
-    const unsigned tHi = __reduce_max_sync(peers, inTop ? r + 1 : 0u);
-    const unsigned lLo = __reduce_min_sync(peers, inLeft ? c : SSG_NIL);
-    const unsigned lHi = __reduce_max_sync(peers, inLeft ? c + 1 : 0u);
-    const bool trim = r >= top && r < bottom && c >= left && c < right;
-    const unsigned anyTrim = __reduce_max_sync(peers, trim ? 1u : 0u);
-    if (leader) {
-        atomicMin(&tb.minRow[s], rMin);
-        atomicMin(&tb.minCol[s], cMin);
-        if (tLo != SSG_NIL) { atomicMin(&tb.tMin[s], tLo); atomicMax(&tb.tMax1[s], tHi); }
-        if (lLo != SSG_NIL) { atomicMin(&tb.lMin[s], lLo); atomicMax(&tb.lMax1[s], lHi); }
-        if (anyTrim) tb.inTrim[s] = 1u;
-    }
+    const bool inTrim = r >= top && r < bottom && cEnd >= left && c < right;
+    // current entries first (independent loads), then only the atomics that change something
+    const unsigned curMinRow = __ldcg(&tb.minRow[s]), curMinCol = __ldcg(&tb.minCol[s]);
+    const unsigned curTMin = inTop ? __ldcg(&tb.tMin[s]) : 0u, curTMax = inTop ? __ldcg(&tb.tMax1[s]) : SSG_NIL;
+    const unsigned curLMin = inLeft ? __ldcg(&tb.lMin[s]) : 0u, curLMax = inLeft ? __ldcg(&tb.lMax1[s]) : SSG_NIL;
+    const unsigned curTrim = inTrim ? __ldcg(&tb.inTrim[s]) : 1u;
+    const unsigned lHi = (cEnd < (unsigned)leftCols ? cEnd : (unsigned)leftCols - 1u) + 1u;
+    if (r < curMinRow) atomicMin(&tb.minRow[s], r);
+    if (c < curMinCol) atomicMin(&tb.minCol[s], c);
+    if (inTop && r < curTMin) atomicMin(&tb.tMin[s], r);
+    if (inTop && r + 1u > curTMax) atomicMax(&tb.tMax1[s], r + 1u);
+    if (inLeft && c < curLMin) atomicMin(&tb.lMin[s], c);
+    if (inLeft && lHi > curLMax) atomicMax(&tb.lMax1[s], lHi);
+    if (curTrim == 0u) tb.inTrim[s] = 1u;
 }
 
 __global__ void __launch_bounds__(256)
