@@ -425,6 +425,16 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         sameMosaic = bool(t.item())
 
+    perRank = None
+    if dist is not None:      # every rank's host timers of its last steps, for the scaling analysis
+        mineT = {'resident': dict((k, round(v['total'] * 1e3, 1)) for (k, v) in
+                    lastRes[0].timings.makeSummaryDict().items()),
+                 'e2e': dict((k, round(v['total'] * 1e3, 1)) for (k, v) in
+                    lastE2E[0].timings.makeSummaryDict().items()),
+                 'tiles': len([cr for cr in tileInfo.tiles if owner[cr] == rank]),
+                 'tile_mpix': round(sum(t[2] * t[3] for (cr, t) in tileInfo.tiles.items() if owner[cr] == rank) / 1e6, 1)}
+        perRank = [None] * world
+        dist.all_gather_object(perRank, mineT)
     if rank == 0:
         (peak, peakKind) = measured_peaks()
         # roofline of the dominant kernel, from the events recorded around every launch
@@ -479,6 +489,7 @@ def run_ours(args, wl):
             'cpu_baseline': cpu, 'clocks': clocks,
             'segments_per_scene': int(lastRes[1]),
             'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastProf[0].stageMs.items()),
+            'per_rank': perRank,
             'host_ms_last_step': {
                 'resident': dict((k, round(v['total'] * 1e3, 2)) for (k, v) in
                     lastRes[0].timings.makeSummaryDict().items()),

@@ -163,8 +163,9 @@ class LazyResolver(object):
         self.offsets = offsets
         self.simple = simple
         self.luts = {}
-        self.missing = set()    # tiles a look-up reached without their table being here
-        self.misses = 0         # how often that happened (a tile can be reached many times)
+        self.misses = 0         # look-ups that could not be answered yet
+        self.remote = {}        # tile of another rank -> (labels ascending, their final ids)
+        self.requests = {}      # tile of another rank -> [label arrays] still to be asked for
 
     def _lutOf(self, cr):
         """the tile's lut with everything that needs no neighbour filled in (one vectorised pass);
@@ -184,9 +185,38 @@ class LazyResolver(object):
             self.luts[cr] = lut
         return self.luts[cr]
 
-    def reset(self):
-        self.luts = {}
-        self.missing = set()
+    def remoteIds(self, cr, labels):
+        """final ids of labels of a tile owned by another rank, from the owner's answers so far;
+        what is not known yet is queued in self.requests.  Returns (ids, complete)."""
+        labels = numpy.asarray(labels, dtype=numpy.int64)
+        out = numpy.zeros(len(labels), dtype=numpy.uint32)
+        found = numpy.zeros(len(labels), dtype=bool)
+        if cr in self.remote:
+            (known, vals) = self.remote[cr]
+            pos = numpy.searchsorted(known, labels)
+            pos[pos >= len(known)] = 0
+            found = known[pos] == labels
+            out[found] = vals[pos[found]]
+        if not found.all():
+            self.requests.setdefault(cr, []).append(labels[~found])
+            return (out, False)
+        return (out, True)
+
+    def addRemote(self, cr, labels, vals):
+        if cr in self.remote:
+            labels = numpy.concatenate([self.remote[cr][0], labels])
+            vals = numpy.concatenate([self.remote[cr][1], vals])
+        order = numpy.argsort(labels, kind='stable')
+        self.remote[cr] = (labels[order].astype(numpy.int64), vals[order].astype(numpy.uint32))
+
+    def answer(self, cr, labels):
+        """what an owner can say about labels of its tile cr right now: (labels, final ids) of
+        those that are settled"""
+        labels = numpy.asarray(labels, dtype=numpy.int64)
+        self.finalIds(cr, labels)
+        vals = self.luts[cr][labels]
+        settled = vals != self.UNKNOWN
+        return (labels[settled], vals[settled])
 
     def finalIds(self, cr, labels):
         """final ids of the given local labels of tile cr (int64 array).  Entries whose value
@@ -218,14 +248,17 @@ class LazyResolver(object):
                 lut[which] = 0
                 continue
             if nb not in self.tables:
-                # noted; the entries stay open until the table has been fetched
-                self.missing.add(nb)
-                self.misses += 1
-                continue
-            before = self.misses
-            mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
-            if self.misses > before:
-                continue          # the neighbour's own answer is still open somewhere below
+                # a tile of another rank: its owner answers (entries stay open until then)
+                (mapped, complete) = self.remoteIds(nb, nbr[sel])
+                if not complete:
+                    self.misses += 1
+                    continue
+                mapped = mapped.astype(numpy.int64)
+            else:
+                before = self.misses
+                mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
+                if self.misses > before:
+                    continue          # the neighbour's own answer is still open somewhere below
             lut[which] = 0
             (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
             lut[k] = mode.astype(numpy.uint32)
@@ -270,6 +303,10 @@ class LocalComm(object):
     def allgatherBytes(self, b):
         """uint8 array (or bytes) from every rank -> list of uint8 arrays"""
         return [numpy.frombuffer(b, dtype=numpy.uint8) if not isinstance(b, numpy.ndarray) else b]
+
+    def allgatherArray(self, a):
+        """int64 array from every rank -> list of int64 arrays"""
+        return [numpy.asarray(a, dtype=numpy.int64)]
 
     def exchange(self, sends, recvs):
         """sends: [(dstRank, tensor)], recvs: [(srcRank, tensor)] in matching order per rank pair"""
@@ -317,6 +354,27 @@ class TorchComm(object):
         out = [self.torch.zeros_like(mine) for _ in range(self.world)]
         self.dist.all_gather(out, mine)
         return [o.cpu().numpy()[:sizes[i]] for (i, o) in enumerate(out)]
+
+    def allgatherArray(self, a, quick=1 << 15):
+        """int64 array from every rank -> list of int64 arrays.  One collective when every rank's
+        array fits `quick` entries (slot 0 carries the length), otherwise the sizes first."""
+        a = numpy.ascontiguousarray(a, dtype=numpy.int64)
+        torch = self.torch
+        if not hasattr(self, '_quickBufs') or self._quickBufs[0].numel() != quick + 1:
+            self._quickBufs = (torch.zeros(quick + 1, dtype=torch.int64, device=self.device),
+                torch.zeros(self.world * (quick + 1), dtype=torch.int64, device=self.device))
+        (mine, everyone) = self._quickBufs
+        host = numpy.zeros(quick + 1, dtype=numpy.int64)
+        host[0] = len(a)
+        if len(a) <= quick:
+            host[1:1 + len(a)] = a
+        mine.copy_(torch.from_numpy(host))
+        self.dist.all_gather_into_tensor(everyone, mine)
+        got = everyone.cpu().numpy().reshape(self.world, quick + 1)
+        sizes = got[:, 0]
+        if (sizes <= quick).all():
+            return [got[r, 1:1 + int(sizes[r])].copy() for r in range(self.world)]
+        return [b.view(numpy.int64) for b in self.allgatherBytes(a.view(numpy.uint8))]
 
     def exchange(self, sends, recvs):
         ops = []
@@ -454,9 +512,9 @@ class ShardedStitch(object):
             step = tb.maxLabelInTrim if self.simple else tb.maxRankInTrim
             mineInts += [cr[0], cr[1], step]
         steps = {}
-        for vals in comm.allgatherInts(mineInts):
+        for vals in comm.allgatherArray(numpy.array(mineInts, dtype=numpy.int64)):
             for i in range(0, len(vals), 3):
-                steps[(vals[i], vals[i + 1])] = vals[i + 2]
+                steps[(int(vals[i]), int(vals[i + 1]))] = int(vals[i + 2])
         offsets = {}
         offset = 0
         for cr in self.order:
@@ -467,37 +525,43 @@ class ShardedStitch(object):
 
     def _resolve(self, tables, steps, offsets, maxSegId):
         comm = self.comm
-        # 4. final ids of own tiles.  Tables of the tiles that a tile on another rank looks into
-        # are fetched on request: first the direct neighbours across a rank boundary, then
-        # whatever the look-ups ask for beyond them (a crossing segment's id can be inherited
-        # through several tiles around a corner).
+        # 4. final ids of own tiles.  A crossing segment takes the final id of the neighbour
+        # segment it overlaps most; when that neighbour tile lives on another rank its OWNER is
+        # asked for the final ids of the labels in question (a few thousand per boundary tile),
+        # and answers what it has settled.  An id inherited through several tiles around a
+        # corner takes one more round per hop.
         luts = {}
-        known = dict(tables)
-        want = set()
-        if not self.simple:
-            for cr in self.mine:
-                for nb in self.neighbours(cr):
-                    if nb is not None and self.owner[nb] != comm.rank:
-                        want.add(nb)
-        resolver = LazyResolver(known, offsets, self.simple)
-        for _round in range(len(self.order) + 2):
-            asked = set()
-            for vals in comm.allgatherInts([v for cr in sorted(want) for v in cr]):
-                asked.update((vals[i], vals[i + 1]) for i in range(0, len(vals), 2))
-            if asked:
-                give = dict((cr, tables[cr]) for cr in asked if cr in tables)
-                for b in comm.allgatherBytes(packTables(give)):
-                    for (cr, tb) in unpackTables(b).items():
-                        if cr not in known:
-                            known[cr] = tb
-            elif luts:
-                break
-            resolver.missing = set()
+        resolver = LazyResolver(dict(tables), offsets, self.simple)
+        for _round in range(len(self.order) + 3):
+            resolver.requests = {}
             for cr in self.mine:          # (entries settled in an earlier round are kept)
                 luts[cr] = resolver.fullLut(cr)
-            want = set(resolver.missing)
+            req = []
+            for (cr, parts) in sorted(resolver.requests.items()):
+                labels = numpy.unique(numpy.concatenate(parts))
+                req += [numpy.array([cr[0], cr[1], len(labels)], dtype=numpy.int64), labels]
+            allReq = comm.allgatherArray(numpy.concatenate(req) if req else numpy.zeros(0, numpy.int64))
+            if not any(len(a) for a in allReq):
+                break
+            ans = []
+            for a in allReq:
+                o = 0
+                while o < len(a):
+                    (c, r, n) = (int(v) for v in a[o:o + 3])
+                    labels = a[o + 3:o + 3 + n]
+                    o += 3 + n
+                    if self.owner[(c, r)] == comm.rank:
+                        (lab, vals) = resolver.answer((c, r), labels)
+                        ans += [numpy.array([c, r, len(lab)], dtype=numpy.int64), lab, vals.astype(numpy.int64)]
+            for a in comm.allgatherArray(numpy.concatenate(ans) if ans else numpy.zeros(0, numpy.int64)):
+                o = 0
+                while o < len(a):
+                    (c, r, n) = (int(v) for v in a[o:o + 3])
+                    if (c, r) in resolver.requests:
+                        resolver.addRemote((c, r), a[o + 3:o + 3 + n], a[o + 3 + n:o + 3 + 2 * n])
+                    o += 3 + 2 * n
         else:
-            raise RuntimeError('sharded stitch: table look-ups did not settle')
+            raise RuntimeError('sharded stitch: look-ups across ranks did not settle')
         # the check of the hypothesis
         ok = 1
         for cr in self.mine:
@@ -505,7 +569,7 @@ class ShardedStitch(object):
             trimmedMax = int(luts[cr][inTrim].max()) if inTrim.any() else 0
             if max(offsets[cr], trimmedMax) != offsets[cr] + steps[cr] or self.forceSequential:
                 ok = 0
-        if min(v[0] for v in comm.allgatherInts([ok])) == 0:
+        if min(int(v[0]) for v in comm.allgatherArray(numpy.array([ok], dtype=numpy.int64))) == 0:
             # some window holds an inherited id above the running maximum: replay the
             # reference's sequential order over all tables, on every rank
             self.usedFallback = True

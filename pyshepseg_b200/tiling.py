@@ -721,6 +721,7 @@ class TiledSegmenter(object):
         stripDev = cudaDev if onDevice else torch.device('cpu')
         seg = self
         keep = []     # device copies of strips received through the host
+        early = {}    # tables computed while the other tiles were still being segmented
 
         class Ops(object):
             def sendStrip(self, cr, which):
@@ -750,6 +751,8 @@ class TiledSegmenter(object):
                 return d
 
             def tables(self, cr, top, left):
+                if cr in early:
+                    return early.pop(cr)
                 t = seg.tiles[cr]
                 (topB, topStride, leftB, leftStride) = (None, 0, None, 0)
                 if top is not None:
@@ -779,6 +782,7 @@ class TiledSegmenter(object):
             self._reserve(main, numWorkers == 0)
             hist.reset(main.ctx)
             self._profileStart(main)
+            ops = Ops()
             with self.timings.interval('segmentation_all'):
                 if numWorkers > 0:
                     inQue = queue.Queue()
@@ -789,19 +793,40 @@ class TiledSegmenter(object):
                             daemon=True)
                         th.start()
                         workers.append(th)
-                    for th in workers:
-                        th.join()
-                    for cr in mine:
-                        if self.tiles[cr].error is not None:
+                for cr in mine:
+                    tile = self.tiles[cr]
+                    if numWorkers > 0:
+                        if not tile.done.wait(cfg.tileCompletionTimeout):
+                            self.forceExit.set()
+                            raise PyShepSegTilingError(("Timeout ({} seconds) waiting for completed "
+                                "tile. Try increasing tileCompletionTimeout").format(cfg.tileCompletionTimeout))
+                        if tile.error is not None:
                             raise PyShepSegTilingError("A segmentation worker failed on tile col={} row={}: {}".format(
-                                cr[0], cr[1], self.tiles[cr].error))
-                else:
-                    for cr in mine:
-                        self.segmentOne(main, pool, self.tiles[cr])
+                                cr[0], cr[1], tile.error))
+                    else:
+                        self.segmentOne(main, pool, tile)
+                    # a tile whose upper and left neighbours are this rank's own (and therefore
+                    # done: they come earlier in the order) gets its tables while the workers go on
+                    (up, left) = stitch.neighbours(cr)
+                    if all(nb is None or stitch.owner[nb] == comm.rank for nb in (up, left)):
+                        early[cr] = ops.tables(cr, None if (up is None or self.simple) else 'local',
+                            None if (left is None or self.simple) else 'local')
+                for th in workers:
+                    th.join()
             with self.timings.interval('stitchtiles'):
-                (maxSegId, offsets, luts) = stitch.run(Ops())
-                histogram = hist.fetch(main.ctx, maxSegId + 1)
-                histogram = comm.allreduceSum(histogram)
+                (maxSegId, offsets, luts) = stitch.run(ops)
+                with self.timings.interval('stitch_histogram'):
+                    n = maxSegId + 1
+                    if onDevice and hist.dev is not None and n <= hist.cap:
+                        # summed over the ranks on the devices, one copy to the host
+                        t = torch.empty(n, dtype=torch.int64, device=cudaDev)
+                        main.ctx.call('ssg_memcpy_d2d', t.data_ptr(), hist.dev, n * 8)
+                        main.ctx.synchronize()
+                        torch.distributed.all_reduce(t)
+                        histogram = t.cpu().numpy().astype(numpy.float64)
+                        histogram[0] = 0
+                    else:
+                        histogram = comm.allreduceSum(hist.fetch(main.ctx, n))
             self.d2hBytes += histogram.nbytes
             self.usedFallback = stitch.usedFallback
         finally:
