@@ -295,10 +295,9 @@ k_apply_lut_window(const unsigned *__restrict__ tile, int64_t xsize, const unsig
     }
     if (!hist) return;
     const bool use = valid && (int64_t)v < histLen;
-    const unsigned active = __ballot_sync(0xffffffffu, use);
-    if (!use) return;
-    const unsigned peers = __match_any_sync(active, v);
-    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[v], (unsigned long long)__popc(peers));
+    // one atomic per run of equal ids in the warp (a run does not continue into the next row)
+    const WarpRuns run = warp_runs(v, use, valid && (t % wCols) == 0);
+    if (run.head) atomicAdd(&hist[v], (unsigned long long)run.len);
 }
 
 extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,

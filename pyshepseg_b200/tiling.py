@@ -701,7 +701,8 @@ class TiledSegmenter(object):
         The tiles of the mosaic dealt over the ranks of `comm` (distributed.ShardedStitch): this
         rank segments its own tiles, keeps their labels in HBM, exchanges overlap strips with the
         ranks that own neighbouring tiles, and writes the trimmed windows of its tiles.
-        Returns (maxSegId, histogram summed over the ranks).
+        Returns (maxSegId, histogram summed over the ranks; on rank 0 only when the ranks
+        talk over NCCL).
         """
         from . import distributed
         import torch
@@ -815,16 +816,22 @@ class TiledSegmenter(object):
                     th.join()
             with self.timings.interval('stitchtiles'):
                 (maxSegId, offsets, luts) = stitch.run(ops)
+                with self.timings.interval('stitch_applywait'):
+                    main.ctx.synchronize()
                 with self.timings.interval('stitch_histogram'):
                     n = maxSegId + 1
                     if onDevice and hist.dev is not None and n <= hist.cap:
-                        # summed over the ranks on the devices, one copy to the host
+                        # summed over the ranks on the devices into rank 0, which alone holds the
+                        # output's histogram (the other ranks return None for it)
                         t = torch.empty(n, dtype=torch.int64, device=cudaDev)
                         main.ctx.call('ssg_memcpy_d2d', t.data_ptr(), hist.dev, n * 8)
                         main.ctx.synchronize()
-                        torch.distributed.all_reduce(t)
-                        histogram = t.cpu().numpy().astype(numpy.float64)
-                        histogram[0] = 0
+                        torch.distributed.reduce(t, 0)
+                        if comm.rank == 0:
+                            histogram = t.cpu().numpy().astype(numpy.float64)
+                            histogram[0] = 0
+                        else:
+                            histogram = numpy.zeros(0)
                     else:
                         histogram = comm.allreduceSum(hist.fetch(main.ctx, n))
             self.d2hBytes += histogram.nbytes
