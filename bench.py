@@ -404,6 +404,9 @@ def run_ours(args, wl):
     # other streams' kernels)
     (msProfiled, lastProf) = timed(resident_profiled, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get('SSG_TIMELINE') and rank == 0:
+        for (ms, what) in sorted(lastE2E[0].timeline):
+            print('  %8.2f  %s' % (ms, what), file=sys.stderr)
 
     pixelsPerStep = nR * nC      # unique pixels of the mosaic (all ranks together)
     value = pixelsPerStep * args.steps / (msResident / 1e3) / 1e6

@@ -55,6 +55,10 @@ typedef struct ssg_ctx ssg_ctx;
 int ssg_abi_version(void);
 int ssg_device_count(void);
 int ssg_ctx_create(int device, ssg_ctx **out);
+/* the same with the context's stream at the device's highest priority: for the short
+ * latency-critical work of a pipeline (the stitch kernels of the tiled driver, which would
+ * otherwise queue behind the segmentation kernels of the worker contexts) */
+int ssg_ctx_create_priority(int device, ssg_ctx **out);
 void ssg_ctx_destroy(ssg_ctx *ctx);
 const char *ssg_last_error(const ssg_ctx *ctx);
 /* the context's cudaStream_t, so a caller can order its own work / events against it */

@@ -62,6 +62,7 @@ SIGNATURES = {
     'ssg_abi_version': (_i, []),
     'ssg_device_count': (_i, []),
     'ssg_ctx_create': (_i, [_i, _c.POINTER(_vp)]),
+    'ssg_ctx_create_priority': (_i, [_i, _c.POINTER(_vp)]),
     'ssg_ctx_destroy': (None, [_vp]),
     'ssg_last_error': (_c.c_char_p, [_vp]),
     'ssg_ctx_stream': (_vp, [_vp]),
@@ -166,11 +167,12 @@ class PinnedArray(object):
 
 class Context(object):
     """One ssg_ctx: a CUDA stream plus scratch memory on one device, used by one thread."""
-    def __init__(self, device=0):
+    def __init__(self, device=0, highPriority=False):
         self.lib = load()
         self.device = int(device)
         h = ctypes.c_void_p()
-        rc = self.lib.ssg_ctx_create(self.device, ctypes.byref(h))
+        create = self.lib.ssg_ctx_create_priority if highPriority else self.lib.ssg_ctx_create
+        rc = create(self.device, ctypes.byref(h))
         if rc != 0 or not h:
             raise ShepsegB200Error('cannot create a CUDA context on device %d (code %d): a B200 '
                 'is required, there is no CPU fallback' % (self.device, rc))

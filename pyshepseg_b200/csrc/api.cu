@@ -17,7 +17,12 @@ int ssg_device_count(void)
     return n;
 }
 
-int ssg_ctx_create(int device, ssg_ctx **out)
+static int ctx_create(int device, int highPriority, ssg_ctx **out);
+
+int ssg_ctx_create(int device, ssg_ctx **out) { return ctx_create(device, 0, out); }
+int ssg_ctx_create_priority(int device, ssg_ctx **out) { return ctx_create(device, 1, out); }
+
+static int ctx_create(int device, int highPriority, ssg_ctx **out)
 {
     if (!out) return SSG_ERR_ARG;
     *out = nullptr;
@@ -29,7 +34,9 @@ int ssg_ctx_create(int device, ssg_ctx **out)
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->numSMs = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SSG_ERR_CUDA; }
+    int prLow = 0, prHigh = 0;
+    cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);     // (numerically lower = more urgent)
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, highPriority ? prHigh : prLow) != cudaSuccess) { delete ctx; return SSG_ERR_CUDA; }
     if (cudaMalloc(&ctx->counters.p, C_COUNT * sizeof(uint64_t)) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return SSG_ERR_NOMEM; }
     ctx->counters.cap = C_COUNT * sizeof(uint64_t);
     cudaMemsetAsync(ctx->counters.p, 0, ctx->counters.cap, ctx->stream);

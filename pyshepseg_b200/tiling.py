@@ -20,9 +20,11 @@ orchestration).
 """
 import atexit
 import ctypes
+import os
 import queue
 import sys
 import threading
+import time
 
 import numpy
 
@@ -280,8 +282,8 @@ class _DevicePool(object):
 class _Slot(object):
     """A context with its staging memory, kept alive between calls: creating contexts and
     pinned / device buffers costs far more than segmenting a tile."""
-    def __init__(self, device):
-        self.ctx = _lib.Context(device)
+    def __init__(self, device, highPriority=False):
+        self.ctx = _lib.Context(device, highPriority)
         self.pinned = None       # PinnedArray staging of one tile image
         self.devStage = None     # (cap, ptr): tile image gathered from a DeviceRaster
         self.window = None       # PinnedArray staging of one trimmed output window
@@ -339,7 +341,8 @@ class _GpuState(object):
     def slot(self, i):
         with self.lock:
             while len(self.slots) <= i:
-                self.slots.append(_Slot(self.device))
+                # slot 0 stitches: short kernels that must not queue behind the workers' long ones
+                self.slots.append(_Slot(self.device, highPriority=(len(self.slots) == 0)))
             return self.slots[i]
 
     def close(self):
@@ -427,10 +430,17 @@ class TiledSegmenter(object):
         self.d2hBytes = 0
         self.kernelMs = {}       # name -> [count, total ms] when profile=True
         self.statLock = threading.Lock()
+        self.timeline = [] if os.environ.get('SSG_TIMELINE') else None   # (ms, what) of one run
+        self.t0 = time.perf_counter()
+
+    def mark(self, what):
+        if self.timeline is not None:
+            self.timeline.append((round((time.perf_counter() - self.t0) * 1e3, 2), what))
 
     # ---- segmentation of one tile on a slot --------------------------------------------------
     def segmentOne(self, slot, pool, tile):
         ctx = slot.ctx
+        self.mark('tile %d,%d read start' % (tile.col, tile.row))
         dtype = self.src.dtype.newbyteorder('=')
         item = dtype.itemsize
         nB = len(self.bandNumbers)
@@ -454,6 +464,7 @@ class TiledSegmenter(object):
                     img = slot.pinnedFor(nB * nPix, dtype).reshape(nB, tile.ysize, tile.xsize)
                     self.src.readWindow(self.bandNumbers, tile.xpos, ypos, tile.xsize, tile.ysize,
                         out=img)
+        self.mark('tile %d,%d read issued' % (tile.col, tile.row))
         with self.timings.interval('segmentation'):
             if direct is None:
                 ctx.call('ssg_upload_image', _lib.ptr(img), _lib.DTYPE_CODES[numpy.dtype(dtype)], nB,
@@ -464,6 +475,7 @@ class TiledSegmenter(object):
                 self.imgNullVal, self.fourConnected, self.minSegmentSize, self.thr)
             res = _lib.TileResult()
             ctx.call('ssg_segment_tile_device', imgDev, ctypes.byref(prm), tile.buf[1], ctypes.byref(res))
+        self.mark('tile %d,%d segmented (dev %.1f ms)' % (tile.col, tile.row, res.msTotal))
         tile.numSegments = int(res.numSegments)
         tile.result = res
         with self.statLock:
@@ -595,6 +607,7 @@ class TiledSegmenter(object):
         self.h2dBytes += lut.nbytes
 
     def stitchOne(self, slot, pool, tile, offset, sink, hist):
+        self.mark('tile %d,%d stitch start' % (tile.col, tile.row))
         ov = self.overlapSize
         up = self.tiles.get((tile.col, tile.row - 1)) if tile.row > 0 else None
         lf = self.tiles.get((tile.col - 1, tile.row)) if tile.col > 0 else None
@@ -615,8 +628,10 @@ class TiledSegmenter(object):
                 None if up is None else up.lut, None if lf is None else lf.lut, self.simple)
         tile.lut = lut
         n = tb.maxId + 1
+        self.mark('tile %d,%d resolved' % (tile.col, tile.row))
         self.applyLut(slot, tile, lut, tb.maxId, sink, hist,
             max(offset + tb.countNew, trimmedMax, int(lut.max()) if n else 0) + 1)
+        self.mark('tile %d,%d window delivered' % (tile.col, tile.row))
         # the neighbours' labels are no longer needed once both users have run
         for nb in (up, lf):
             if nb is not None:
@@ -651,6 +666,9 @@ class TiledSegmenter(object):
             hist.reset(main.ctx)
             self._profileStart(main)
             if numWorkers > 0:
+                # (row-major, the order of the stitch: starting the large corner tile first was
+                # measured to be slower -- the GPU is the shared resource, and the small first
+                # tiles then finish late and hold up the whole stitch chain)
                 inQue = queue.Queue()
                 for cr in self.order:
                     inQue.put(cr)
