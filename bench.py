@@ -462,7 +462,7 @@ def run_ours(args, wl):
             roof['timed_in'] = ('%d single-stream steps after the timed region, event pair per launch '
                 '(%.1f ms per step)' % (args.steps, msProfiled / args.steps))
         kernels = dict((k, {'launches': v[0], 'ms': round(v[1], 3)}) for (k, v) in sorted(kernelAgg.items(),
-            key=lambda kv: -kv[1][1])[:12])
+            key=lambda kv: -kv[1][1])[:24])
         # secondary rooflines of the two bandwidth kernels the north star names
         extra = {}
         for name in ('k_assign', 'k_ccl_local'):

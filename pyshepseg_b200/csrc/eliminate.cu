@@ -881,6 +881,7 @@ k_small_persistent(SmallState st)
     int selSet = 0;
     unsigned long long selLo = 0, selHi = 0;   // selList[selSet] range: the grown segments of size t
     for (int t = 1; t < st.minSegSize; t++) {
+        const long long tStart = clock64();
         CandSource src;
         src.a = st.bucketList + st.bucketStart[t];
         src.na = st.bucketStart[t + 1] - st.bucketStart[t];
@@ -928,6 +929,10 @@ k_small_persistent(SmallState st)
         } else if (t + 1 >= st.minSegSize) {
             selLo = selHi = 0;
         }
+        if (dbgOn && t < 112) {
+            st.dbg[16 + 2 * t] = (unsigned long long)(clock64() - tStart);
+            st.dbg[16 + 2 * t + 1] = src.na + src.nb + src.nr;
+        }
     }
     if (gtid == 0) st.ctr[SC_PASSES] = passes;
     if (dbgOn)
@@ -965,6 +970,12 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses, i
         fprintf(stderr, "  small: %llu small segments, %llu arena pixels of %u, %llu grown\n",
                 (unsigned long long)st.cap, (unsigned long long)host[SC_ARENA], st.arenaCap,
                 (unsigned long long)host[SC_GROWN]);
+        unsigned long long pt[240];
+        SSG_CUDA(ctx, cudaMemcpy(pt, st.dbg, sizeof(pt), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "  small: us per target size (last list length):");
+        for (int t = 1; t < st.minSegSize && t < 112; t++)
+            fprintf(stderr, "%s %d:%.0f(%llu)", (t % 8 == 1) ? "\n   " : "", t, pt[16 + 2 * t] / 1965.0, pt[16 + 2 * t + 1]);
+        fprintf(stderr, "\n");
     }
     return SSG_OK;
 }
@@ -1067,7 +1078,7 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     st.arenaBase = (unsigned)numSmallPix; st.arenaCap = (unsigned)arenaCap;
     st.dbg = nullptr;
     if (getenv("SSG_SMALL_DEBUG")) {   // phase timing of the persistent kernel, to stderr
-        SSG_TRY(ssg_reserve(ctx, ctx->targetList, 16 * sizeof(unsigned long long)));
+        SSG_TRY(ssg_reserve(ctx, ctx->targetList, 240 * sizeof(unsigned long long)));
         st.dbg = bufp<unsigned long long>(ctx->targetList);
     }
     st.nB = nB; st.nRows = nRows; st.nCols = nCols; st.four = four;

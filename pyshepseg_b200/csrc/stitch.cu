@@ -19,12 +19,24 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 
+// What the stitch asks about a segment are all questions of existence -- "is a pixel of it left
+// of the trimmed window", "does it have pixels on both sides of the overlap midline" -- so the
+// per-segment tables are bytes that any pixel of the segment may set to 1: plain stores, no
+// atomics, no read-modify-write.
+//   bbox corner inside the trimmed window (tiling.py:1255-1265):
+//     minCol >= left  <=> no pixel with c < left        minRow >= top    <=> no pixel with r < top
+//     minCol <  right <=> some pixel with c < right      minRow <  bottom <=> some pixel with r < bottom
+//   crossesMidline (tiling.py:1303-1306): min < mid <= max over the strip
+//     <=> some strip pixel before the midline and some strip pixel at or after it.
 struct StitchTables {
-    unsigned *minRow, *minCol;     // bbox corner over the whole tile
-    unsigned *tMin, *tMax1;        // row extent inside the top strip (max stored +1)
-    unsigned *lMin, *lMax1;        // column extent inside the left strip
-    unsigned *inTrim;
+    unsigned char *interior;       // has a pixel inside the trimmed window
+    unsigned char *margin;         // has a pixel outside it
+    unsigned char *leftOf, *above; // has a pixel with c < left / r < top
+    unsigned char *ltRight, *ltBottom;   // has a pixel with c < right / r < bottom
+    unsigned char *topA, *topB;    // top strip: pixel with r < mid / mid <= r < strip rows
+    unsigned char *leftA, *leftB;  // left strip: pixel with c < mid / mid <= c < strip columns
 };
+#define STITCH_TABLES 10
 
 __global__ void __launch_bounds__(256)
 k_tile_max(const unsigned *__restrict__ tile, int64_t N, unsigned long long *counters)
@@ -48,8 +60,8 @@ k_tile_max(const unsigned *__restrict__ tile, int64_t N, unsigned long long *cou
 }
 
 __global__ void __launch_bounds__(256)
-k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, int64_t topRows,
-               int64_t leftCols, int64_t top, int64_t bottom, int64_t left, int64_t right,
+k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, unsigned topRows,
+               unsigned leftCols, unsigned top, unsigned bottom, unsigned left, unsigned right,
                StitchTables tb)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,46 +69,51 @@ k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, 
     const unsigned s = valid ? tile[p] : 0u;
     const bool use = valid && s != 0;
     const unsigned r = (unsigned)(p / xsize), c = (unsigned)(p % xsize);
-    // runs of equal labels inside one raster row: the head lane knows the run's row and its first
-    // and last column, which is all the extents need -- no reductions.  A table entry is only
-    // touched when the run can improve it (most runs lie below / right of the segment's corner).
+    // a run of equal labels inside one raster row: its head lane knows the row and the first and
+    // last column, and speaks for the whole run
     const WarpRuns run = warp_runs(s, use, c == 0);
     if (!run.head) return;
     const unsigned cEnd = c + run.len - 1u;
-    const bool inTop = r < topRows, inLeft = c < leftCols;
-    const bool inTrim = r >= top && r < bottom && cEnd >= left && c < right;
-    // current entries first (independent loads), then only the atomics that change something
-    const unsigned curMinRow = __ldcg(&tb.minRow[s]), curMinCol = __ldcg(&tb.minCol[s]);
-    const unsigned curTMin = inTop ? __ldcg(&tb.tMin[s]) : 0u, curTMax = inTop ? __ldcg(&tb.tMax1[s]) : SSG_NIL;
-    const unsigned curLMin = inLeft ? __ldcg(&tb.lMin[s]) : 0u, curLMax = inLeft ? __ldcg(&tb.lMax1[s]) : SSG_NIL;
-    const unsigned curTrim = inTrim ? __ldcg(&tb.inTrim[s]) : 1u;
-    const unsigned lHi = (cEnd < (unsigned)leftCols ? cEnd : (unsigned)leftCols - 1u) + 1u;
-    if (r < curMinRow) atomicMin(&tb.minRow[s], r);
-    if (c < curMinCol) atomicMin(&tb.minCol[s], c);
-    if (inTop && r < curTMin) atomicMin(&tb.tMin[s], r);
-    if (inTop && r + 1u > curTMax) atomicMax(&tb.tMax1[s], r + 1u);
-    if (inLeft && c < curLMin) atomicMin(&tb.lMin[s], c);
-    if (inLeft && lHi > curLMax) atomicMax(&tb.lMax1[s], lHi);
-    if (curTrim == 0u) tb.inTrim[s] = 1u;
+    const bool rowInTrim = r >= top && r < bottom;
+    const bool touchesTrim = rowInTrim && cEnd >= left && c < right;
+    const bool allInTrim = rowInTrim && c >= left && cEnd < right;
+    if (touchesTrim) tb.interior[s] = 1;
+    if (!allInTrim) {
+        // the frame around the trimmed window (a few percent of the pixels)
+        tb.margin[s] = 1;
+        if (c < left) tb.leftOf[s] = 1;
+        if (r < top) tb.above[s] = 1;
+        if (c < right) tb.ltRight[s] = 1;
+        if (r < bottom) tb.ltBottom[s] = 1;
+    }
+    if (r < topRows) {
+        if (r < topRows / 2) tb.topA[s] = 1; else tb.topB[s] = 1;
+    }
+    if (c < leftCols) {
+        const unsigned mid = leftCols / 2;
+        if (c < mid) tb.leftA[s] = 1;
+        if (cEnd >= mid) tb.leftB[s] = 1;      // (c < leftCols and cEnd >= mid: a pixel in [mid, leftCols))
+    }
 }
 
 __global__ void __launch_bounds__(256)
-k_tile_flags(StitchTables tb, int64_t len, int hasTop, int hasLeft, unsigned midT, unsigned midL,
-             int64_t top, int64_t bottom, int64_t left, int64_t right, unsigned char *flags,
+k_tile_flags(StitchTables tb, int64_t len, int hasTop, int hasLeft, unsigned char *flags,
              unsigned *numbered)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= len) return;
     unsigned f = 0, num = 0;
-    if (s != 0 && tb.minRow[s] != SSG_NIL) {
+    const bool interior = tb.interior[s] != 0;
+    if (s != 0 && (interior || tb.margin[s])) {
         f |= SSG_SEG_PRESENT;
-        // crossesMidline: min < mid and max >= mid (tiling.py:1303-1306)
-        if (hasTop && tb.tMin[s] < midT && tb.tMax1[s] > midT) f |= SSG_SEG_KEYTOP;
-        if (hasLeft && tb.lMin[s] < midL && tb.lMax1[s] > midL) f |= SSG_SEG_KEYLEFT;
-        if (tb.inTrim[s]) f |= SSG_SEG_INTRIM;
-        const int64_t segLeft = tb.minCol[s], segTop = tb.minRow[s];
-        if (!(f & (SSG_SEG_KEYTOP | SSG_SEG_KEYLEFT)) && segLeft >= left && segTop >= top &&
-            segLeft < right && segTop < bottom) {   // tiling.py:1264-1265
+        if (hasTop && tb.topA[s] && tb.topB[s]) f |= SSG_SEG_KEYTOP;
+        if (hasLeft && tb.leftA[s] && tb.leftB[s]) f |= SSG_SEG_KEYLEFT;
+        if (interior) f |= SSG_SEG_INTRIM;
+        // the corner of the bounding box lies inside the trimmed window (tiling.py:1264-1265);
+        // a pixel inside the window is itself left of `right` and above `bottom`
+        const bool cornerIn = !tb.leftOf[s] && !tb.above[s] && (interior || tb.ltRight[s]) &&
+                              (interior || tb.ltBottom[s]);
+        if (!(f & (SSG_SEG_KEYTOP | SSG_SEG_KEYLEFT)) && cornerIn) {
             f |= SSG_SEG_NUMBERED;
             num = 1;
         }
@@ -140,18 +157,17 @@ k_collect_pairs(const unsigned *__restrict__ tile, int64_t xsize, int64_t stripR
 static int reserveTables(ssg_ctx *ctx, int64_t len, StitchTables &tb, unsigned **numbered,
                          unsigned **excl, unsigned **rank, unsigned char **flags)
 {
-    const size_t n = (size_t)len;
-    SSG_TRY(ssg_reserve(ctx, ctx->stitch0, n * 7 * sizeof(unsigned)));
-    SSG_TRY(ssg_reserve(ctx, ctx->stitch1, n * 3 * sizeof(unsigned) + n));
-    unsigned *base = bufp<unsigned>(ctx->stitch0);
-    tb.minRow = base; tb.minCol = base + n; tb.tMin = base + 2 * n; tb.lMin = base + 3 * n;
-    tb.tMax1 = base + 4 * n; tb.lMax1 = base + 5 * n; tb.inTrim = base + 6 * n;
+    const size_t n = ((size_t)len + 15) & ~(size_t)15;
+    SSG_TRY(ssg_reserve(ctx, ctx->stitch0, n * STITCH_TABLES));
+    SSG_TRY(ssg_reserve(ctx, ctx->stitch1, (size_t)len * 3 * sizeof(unsigned) + (size_t)len));
+    unsigned char *base = bufp<unsigned char>(ctx->stitch0);
+    tb.interior = base; tb.margin = base + n; tb.leftOf = base + 2 * n; tb.above = base + 3 * n;
+    tb.ltRight = base + 4 * n; tb.ltBottom = base + 5 * n; tb.topA = base + 6 * n; tb.topB = base + 7 * n;
+    tb.leftA = base + 8 * n; tb.leftB = base + 9 * n;
     unsigned *b1 = bufp<unsigned>(ctx->stitch1);
-    *numbered = b1; *excl = b1 + n; *rank = b1 + 2 * n;
-    *flags = reinterpret_cast<unsigned char *>(b1 + 3 * n);
-    // the four "min" tables start at NIL, the rest at 0
-    SSG_CUDA(ctx, cudaMemsetAsync(base, 0xFF, n * 4 * sizeof(unsigned), ctx->stream));
-    SSG_CUDA(ctx, cudaMemsetAsync(base + 4 * n, 0, n * 3 * sizeof(unsigned), ctx->stream));
+    *numbered = b1; *excl = b1 + len; *rank = b1 + 2 * len;
+    *flags = reinterpret_cast<unsigned char *>(b1 + 3 * len);
+    SSG_CUDA(ctx, cudaMemsetAsync(base, 0, n * STITCH_TABLES, ctx->stream));
     return SSG_OK;
 }
 
@@ -189,14 +205,14 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     const int64_t topRows = topBDev ? (overlap < ysize ? overlap : ysize) : 0;
     const int64_t leftCols = leftBDev ? (overlap < xsize ? overlap : xsize) : 0;
     SSG_PROF_BEGIN(ctx, "k_tile_extents");
-    k_tile_extents<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, ysize, xsize, topRows, leftCols, top, bottom,
-                                                            left, right, tb);
+    k_tile_extents<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, ysize, xsize, (unsigned)topRows, (unsigned)leftCols,
+                                                            (unsigned)top, (unsigned)bottom, (unsigned)left,
+                                                            (unsigned)right, tb);
     SSG_LAUNCHED(ctx);
     // mid = int(n / 2) of the strip's stitch axis (tiling.py:1297,1300)
     SSG_PROF_BEGIN(ctx, "k_tile_flags");
-    k_tile_flags<<<gridFor(len, 256), 256, 0, ctx->stream>>>(tb, len, topBDev != nullptr, leftBDev != nullptr,
-                                                            (unsigned)(topRows / 2), (unsigned)(leftCols / 2), top,
-                                                            bottom, left, right, flags, numbered);
+    k_tile_flags<<<gridFor(len, 256), 256, 0, ctx->stream>>>(tb, len, topBDev != nullptr, leftBDev != nullptr, flags,
+                                                            numbered);
     SSG_LAUNCHED(ctx);
     size_t tmpBytes = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, numbered, excl, (int)len, ctx->stream));

@@ -207,19 +207,29 @@ def _modeByKey(keys, values, counts):
     """
     For every distinct key: the value with the largest summed count, smallest value on ties
     (scipy.stats.mode over the expanded list, tiling.py:1194).  Returns (keys, modes).
+    keys < 2**31 and values < 2**32 (segment ids), so (key, value) packs into one sortable word.
     """
-    order = numpy.lexsort((values, keys))
-    (k, v, c) = (keys[order], values[order], counts[order].astype(numpy.int64))
-    newGroup = numpy.ones(len(k), dtype=bool)
-    newGroup[1:] = (k[1:] != k[:-1]) | (v[1:] != v[:-1])
+    packed = (keys.astype(numpy.uint64) << numpy.uint64(32)) | values.astype(numpy.uint64)
+    order = numpy.argsort(packed, kind='stable')
+    p = packed[order]
+    c = counts[order].astype(numpy.int64)
+    newGroup = numpy.ones(len(p), dtype=bool)
+    newGroup[1:] = p[1:] != p[:-1]
     starts = numpy.flatnonzero(newGroup)
-    (gk, gv, gc) = (k[starts], v[starts], numpy.add.reduceat(c, starts))
-    # inside one key the groups are in ascending value order; the first maximal count wins
-    best = numpy.lexsort((gv, -gc, gk))
-    firstOfKey = numpy.ones(len(best), dtype=bool)
-    firstOfKey[1:] = gk[best][1:] != gk[best][:-1]
-    sel = best[firstOfKey]
-    return (gk[sel], gv[sel])
+    gp = p[starts]                                  # one entry per (key, value), ascending
+    gc = numpy.add.reduceat(c, starts)
+    gk = (gp >> numpy.uint64(32)).astype(numpy.int64)
+    newKey = numpy.ones(len(gk), dtype=bool)
+    newKey[1:] = gk[1:] != gk[:-1]
+    keyStarts = numpy.flatnonzero(newKey)
+    best = numpy.maximum.reduceat(gc, keyStarts)    # the largest count of every key ...
+    keyOfGroup = numpy.cumsum(newKey) - 1
+    isBest = numpy.flatnonzero(gc == best[keyOfGroup])
+    # ... and the first group that reaches it (groups of a key are in ascending value order)
+    firstOfKey = numpy.ones(len(isBest), dtype=bool)
+    firstOfKey[1:] = keyOfGroup[isBest][1:] != keyOfGroup[isBest][:-1]
+    sel = isBest[firstOfKey]
+    return (gk[sel], (gp[sel] & numpy.uint64(0xFFFFFFFF)).astype(numpy.int64))
 
 
 def resolveTile(tables, rank, flags, pairKeys, pairCounts, offset, lutTop, lutLeft,
@@ -337,6 +347,7 @@ class _GpuState(object):
         self.pool = _DevicePool()
         self.lock = threading.Lock()
         self.hist = _DeviceHistogram()
+        self.rasterBuf = None      # (cap, ptr): device copy of a host raster being segmented
 
     def slot(self, i):
         with self.lock:
@@ -347,6 +358,9 @@ class _GpuState(object):
 
     def close(self):
         if self.slots:
+            if self.rasterBuf is not None:
+                self.slots[0].ctx.dev_free(self.rasterBuf[1])
+                self.rasterBuf = None
             self.hist.close(self.slots[0].ctx)
             self.pool.close(self.slots[0].ctx)
         for sl in self.slots:
@@ -374,6 +388,86 @@ def releaseGpuState():
 
 
 atexit.register(releaseGpuState)
+
+
+class _RasterUploader(object):
+    """
+    A host raster that can be addressed in place goes to the GPU ONCE instead of tile by tile:
+    overlapping tiles share 20-60 % of their pixels, and PCIe is the slowest link of the
+    host-to-host path.  The raster is cut along every tile edge into cells; the cells go up in the
+    order in which the tiles need them (a stream of its own), and a tile is gathered out of the
+    device copy (device-to-device) as soon as its cells have landed.
+    """
+    def __init__(self, slot, hostBase, bandNumbers, ysize, xsize, item, devPtr, tiles, yoff):
+        self.slot = slot
+        self.hostBase = hostBase
+        self.planes = [b - 1 for b in bandNumbers]      # planes of the host raster, in order
+        (self.ysize, self.xsize, self.item) = (ysize, xsize, item)
+        self.devPtr = devPtr                             # (len(bandNumbers), ysize, xsize)
+        # tiles: [(key, xpos, ypos - yoff, xsize, ysize)] in the order they will be segmented
+        self.tiles = [(k, x, y - yoff, xs, ys) for (k, x, y, xs, ys) in tiles]
+        xs = sorted(set([0, xsize] + [t[1] for t in self.tiles] + [t[1] + t[3] for t in self.tiles]))
+        ys = sorted(set([0, ysize] + [t[2] for t in self.tiles] + [t[2] + t[4] for t in self.tiles]))
+        (self.xEdges, self.yEdges) = (xs, ys)
+        self.ready = set()
+        self.cond = threading.Condition()
+        self.error = None
+        self.bytes = 0
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def start(self):
+        self.thread.start()
+
+    def _cellsOf(self, t):
+        (k, x, y, xs, ys) = t
+        for (y0, y1) in zip(self.yEdges[:-1], self.yEdges[1:]):
+            if y0 >= y + ys or y1 <= y:
+                continue
+            for (x0, x1) in zip(self.xEdges[:-1], self.xEdges[1:]):
+                if x0 >= x + xs or x1 <= x:
+                    continue
+                yield (x0, y0, x1, y1)
+
+    def _run(self):
+        try:
+            ctx = self.slot.ctx
+            done = set()
+            pitch = self.xsize * self.item
+            with self.slot.lock:
+                for t in self.tiles:
+                    n = 0
+                    for cell in self._cellsOf(t):
+                        if cell in done:
+                            continue
+                        done.add(cell)
+                        (x0, y0, x1, y1) = cell
+                        for (i, pl) in enumerate(self.planes):
+                            ctx.call('ssg_memcpy2d_h2d',
+                                self.devPtr + (i * self.ysize + y0) * pitch + x0 * self.item, pitch,
+                                self.hostBase + (pl * self.ysize + y0) * pitch + x0 * self.item, pitch,
+                                (x1 - x0) * self.item, y1 - y0)
+                        n += (x1 - x0) * (y1 - y0) * self.item * len(self.planes)
+                    if n:
+                        ctx.synchronize()
+                    with self.cond:
+                        self.ready.add(t[0])
+                        self.bytes += n
+                        self.cond.notify_all()
+        except Exception as e:
+            with self.cond:
+                self.error = e
+                self.cond.notify_all()
+
+    def waitTile(self, key, timeout):
+        with self.cond:
+            ok = self.cond.wait_for(lambda: key in self.ready or self.error is not None, timeout)
+            if self.error is not None:
+                raise self.error
+            if not ok:
+                raise PyShepSegTilingError('timeout waiting for the raster upload')
+
+    def join(self):
+        self.thread.join()
 
 
 class _Tile(object):
@@ -430,6 +524,7 @@ class TiledSegmenter(object):
         self.d2hBytes = 0
         self.kernelMs = {}       # name -> [count, total ms] when profile=True
         self.statLock = threading.Lock()
+        self.uploader = None     # _RasterUploader while a run streams the whole raster to the GPU
         self.timeline = [] if os.environ.get('SSG_TIMELINE') else None   # (ms, what) of one run
         self.t0 = time.perf_counter()
 
@@ -454,8 +549,13 @@ class TiledSegmenter(object):
                 (base, onDevice) = direct
                 imgDev = slot.devStageFor(nB * nPix * item)
                 copy = 'ssg_memcpy2d_d2d' if onDevice else 'ssg_memcpy2d_h2d'
+                up = self.uploader
+                if up is not None:      # the raster is on its way to the device in one piece
+                    up.waitTile((tile.col, tile.row), self.cfg.tileCompletionTimeout)
+                    (base, copy) = (up.devPtr, 'ssg_memcpy2d_d2d')
                 for (i, b) in enumerate(self.bandNumbers):
-                    srcPtr = base + ((b - 1) * self.src.ysize * self.src.xsize +
+                    plane = i if up is not None else b - 1
+                    srcPtr = base + (plane * self.src.ysize * self.src.xsize +
                         ypos * self.src.xsize + tile.xpos) * item
                     ctx.call(copy, imgDev + i * nPix * item, tile.xsize * item, srcPtr,
                         self.src.xsize * item, tile.xsize * item, tile.ysize)
@@ -479,10 +579,36 @@ class TiledSegmenter(object):
         tile.numSegments = int(res.numSegments)
         tile.result = res
         with self.statLock:
-            if not isinstance(self.src, DeviceRaster):
+            if not isinstance(self.src, DeviceRaster) and self.uploader is None:
                 self.h2dBytes += nB * nPix * item
             for k in self.stageMs:
                 self.stageMs[k] += getattr(res, 'ms' + k.capitalize())
+
+    def _startUpload(self, state, slotIndex, order=None):
+        """Stream the raster to the device in one piece (see _RasterUploader) when it is host
+        memory addressable in place and several workers overlap the copy with the kernels."""
+        direct = self._directSource()
+        if direct is None or direct[1] or os.environ.get('SSG_NO_RASTER_UPLOAD'):
+            return
+        dtype = self.src.dtype.newbyteorder('=')
+        nbytes = len(self.bandNumbers) * self.src.ysize * self.src.xsize * dtype.itemsize
+        slot = state.slot(slotIndex)
+        if state.rasterBuf is None or state.rasterBuf[0] < nbytes:
+            if state.rasterBuf is not None:
+                slot.ctx.dev_free(state.rasterBuf[1])
+            state.rasterBuf = (nbytes, slot.ctx.dev_alloc(nbytes))
+        order = self.order if order is None else order
+        tiles = [(cr, self.tiles[cr].xpos, self.tiles[cr].ypos, self.tiles[cr].xsize, self.tiles[cr].ysize)
+            for cr in order]
+        self.uploader = _RasterUploader(slot, direct[0], self.bandNumbers, self.src.ysize, self.src.xsize,
+            dtype.itemsize, state.rasterBuf[1], tiles, getattr(self.src, 'yoff', 0))
+        self.uploader.start()
+
+    def _finishUpload(self):
+        if self.uploader is not None:
+            self.uploader.join()
+            self.h2dBytes += self.uploader.bytes
+            self.uploader = None
 
     def _directSource(self):
         """(base pointer, on device?) when tile windows can be copied straight out of the
@@ -621,6 +747,8 @@ class TiledSegmenter(object):
                 leftB = lf.buf[1] + (lf.xsize - ov) * 4
                 leftStride = lf.xsize
         tb = self.tileTables(slot, tile, topB, topStride, leftB, leftStride)
+        self.mark('tile %d,%d tables on host (%d segments, %d votes)' % (tile.col, tile.row, tb.maxId,
+            len(tb.pairKeys)))
         tables = _lib.TileTables()
         (tables.maxId, tables.countNew, tables.numPairs) = (tb.maxId, tb.countNew, len(tb.pairKeys))
         with self.timings.interval('stitch_resolve'):
@@ -673,6 +801,7 @@ class TiledSegmenter(object):
                 for cr in self.order:
                     inQue.put(cr)
                 with self.timings.interval('startworkers'):
+                    self._startUpload(state, numWorkers + 1)
                     for w in range(numWorkers):
                         th = threading.Thread(target=self._worker, args=(state.slot(1 + w), pool, inQue),
                             daemon=True)
@@ -702,6 +831,7 @@ class TiledSegmenter(object):
             self.forceExit.set()
             for th in workers:
                 th.join()
+            self._finishUpload()
             try:
                 self._profileStop(main)
                 for t in self.tiles.values():
@@ -807,6 +937,7 @@ class TiledSegmenter(object):
                     inQue = queue.Queue()
                     for cr in mine:
                         inQue.put(cr)
+                    self._startUpload(state, numWorkers + 1, mine)
                     for w in range(numWorkers):
                         th = threading.Thread(target=self._worker, args=(state.slot(1 + w), pool, inQue),
                             daemon=True)
@@ -858,6 +989,7 @@ class TiledSegmenter(object):
             self.forceExit.set()
             for th in workers:
                 th.join()
+            self._finishUpload()
             try:
                 self._profileStop(main)
                 for t in self.tiles.values():

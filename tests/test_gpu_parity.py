@@ -152,6 +152,25 @@ def test_against_oracle(shepseg, case):
     _against_oracle(shepseg, img, k, minSeg, 0 if nullFrac > 0 else None, four, msd, name)
 
 
+BASELINE_CASES = [
+    # BASELINE.json configs at sizes the oracle does in ~10 s: C3 (Landsat-like, 6 bands, nodata
+    # wedge, k=30, minSegmentSize=100, fixed centres) and C5 (10-band stack, 'auto', minSeg 50)
+    ('C3_landsat_like_6band_null', (5000, 4400, 6), 30, 100, 0.10, True, 'auto'),
+    ('C5_ten_band_auto', (3600, 3000, 10), 60, 50, 0.0, True, 'auto'),
+]
+
+
+@pytest.mark.parametrize('case', BASELINE_CASES, ids=[c[0] for c in BASELINE_CASES])
+def test_baseline_configs_against_oracle(shepseg, case):
+    (name, (r, c, b), k, minSeg, nullFrac, four, msd) = case
+    img = synth.synth_tiled(r, c, b, seed=len(name))
+    if nullFrac > 0:
+        rr = numpy.arange(r)[:, None]
+        cc = numpy.arange(c)[None, :]
+        img[:, (rr + cc) < numpy.sqrt(2.0 * nullFrac * r * c)] = 0
+    _against_oracle(shepseg, img, k, minSeg, 0 if nullFrac > 0 else None, four, msd, name)
+
+
 def test_flat_cells_over_cap(shepseg):
     """Voronoi cells of constant colour, like the reference's own runtests image
     (cmdline/runtests.py:145-265): every region is far over MAX_CLUMP_SIZE."""

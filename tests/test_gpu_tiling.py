@@ -85,6 +85,9 @@ CASES = [
     ('wide_2000x2600', (2000, 2600, 4), 512, 128, 40, 40, 0.0, True),
     ('null_1500x1700_8conn', (1500, 1700, 3), 400, 100, 30, 30, 0.15, False),
     ('small_overlap', (1300, 1200, 3), 300, 20, 20, 25, 0.0, True),
+    # the tile layout of BASELINE config 2 (10980 with 4096/1024: 2 x 2 tiles, the last row and
+    # column grown to 7908) at a quarter of the size: 2745 with 1024/256 -> tiles of 1024 and 1977
+    ('c2_layout_quarter', (2745, 2745, 4), 1024, 256, 60, 50, 0.0, True),
 ]
 
 
