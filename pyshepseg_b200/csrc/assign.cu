@@ -197,7 +197,10 @@ static int launch_assign(ssg_ctx *ctx, const void *img, int64_t N, const double 
         SSG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t nGroups = (N + V - 1) / V;
     int64_t blocks = (nGroups + 255) / 256;
-    int64_t cap = (int64_t)ctx->numSMs * 64;   // grid-stride beyond this; keeps the centre prologue amortised
+    // a few resident waves, grid-stride beyond: every block first builds the centre tables in
+    // shared memory (float64 norms, two barriers), which with one block per 2048 pixels was a
+    // tenth of the kernel (ncu: barrier stalls)
+    int64_t cap = (int64_t)ctx->numSMs * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     SSG_PROF_BEGIN(ctx, "k_assign");
