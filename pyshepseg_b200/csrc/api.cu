@@ -359,15 +359,6 @@ int ssg_eliminate_small_segments(ssg_ctx *ctx, uint32_t *seg, const void *img, i
 }
 
 // ---- the fused tile pipeline -------------------------------------------------------------------
-__global__ void k_count_zero_sizes(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
-                                   unsigned long long *counter)
-{
-    const int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool hit = s < len && segSize[s] == 0;
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
-}
-
 static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_params *prm,
                              uint32_t *segDev, ssg_tile_result *res)
 {
@@ -395,31 +386,33 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     SSG_TRY(ssgk_eliminate_single(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev,
                                   segSize, len, prm->fourConnected, &moved, &rounds,
                                   numSingles >= 0 ? bufp<unsigned>(ctx->singles) : nullptr, numSingles));
-    // ids that lost their only pixel = what the reference reports as singlePixelsEliminated
-    // (oldMaxSegId - seg.max() after its order-preserving relabel, shepseg.py:226-227)
-    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, sizeof(unsigned long long), ctx->stream));
+    // the reference relabels here (eliminateSinglePixels ends with relabelSegments,
+    // shepseg.py:615), and so do we: three quarters of the clump ids are gone, and every table
+    // of the next stage is that much smaller (they then sit in L2 instead of HBM).
+    // singlePixelsEliminated = oldMaxSegId - seg.max() (shepseg.py:226-227)
+    uint32_t afterSingles = numClumps;
     if (numClumps > 0) {
-        SSG_PROF_BEGIN(ctx, "k_count_zero_sizes");
-        k_count_zero_sizes<<<gridFor(numClumps, 256), 256, 0, ctx->stream>>>(segSize, 1, len, counters + C_SCRATCH1);
-        SSG_LAUNCHED(ctx);
+        SSG_TRY(ssg_reserve(ctx, ctx->aux2, (size_t)len * sizeof(unsigned)));
+        unsigned *compact = bufp<unsigned>(ctx->aux2);
+        SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &afterSingles, compact));
+        segSize = compact;
     }
+    const int64_t len1 = (int64_t)afterSingles + 1;
     SSG_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
 
-    // ids are not compacted between the two elimination stages: the reference's relabel is
-    // order preserving, so the merge order (ascending id) is unchanged
     int64_t numElim = 0;
     uint32_t passes = 0, alive = 0;
     SSG_TRY(ssgk_eliminate_small(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev, segSize,
-                                 numClumps, prm->minSegSize, prm->spectralThreshold, prm->fourConnected,
+                                 afterSingles, prm->minSegSize, prm->spectralThreshold, prm->fourConnected,
                                  &numElim, &passes));
-    SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &alive));
+    SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len1, 1, &alive));
     SSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     SSG_TRY(ssg_fetch_counters(ctx));
 
     res->numClumps = numClumps;
     res->numOversized = numOver;
     res->numSegments = alive;
-    res->singlePixelsEliminated = (uint32_t)ctx->hostCounters[C_SCRATCH1];
+    res->singlePixelsEliminated = numClumps - afterSingles;
     res->smallSegmentsEliminated = numElim;
     res->numSinglePixelRounds = rounds;
     res->numSmallPasses = passes;

@@ -343,5 +343,6 @@ int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands
                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, uint32_t maxSegId,
                          int minSegSize, double thr, int four, int64_t *numElim,
                          uint32_t *numPasses);
+// sizeOutDev (optional, len entries, must not alias sizeDev): the sizes under the new numbering
 int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
-                 uint32_t minSegId, uint32_t *numAlive);
+                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev = nullptr);

@@ -249,8 +249,19 @@ k_apply_lut(unsigned *seg, int64_t N, const unsigned *__restrict__ lut)
     }
 }
 
+// sizes of the surviving ids at their new positions (segSize of the compacted numbering)
+__global__ void __launch_bounds__(256)
+k_compact_sizes(const unsigned *__restrict__ segSize, const unsigned *__restrict__ lut, int64_t len,
+                unsigned minSegId, unsigned *sizeOut)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    const unsigned z = segSize[s];
+    if (s < minSegId || z != 0) sizeOut[lut[s]] = z;
+}
+
 int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
-                 uint32_t minSegId, uint32_t *numAlive)
+                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev)
 {
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
     *numAlive = 0;
@@ -273,6 +284,11 @@ int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *size
     if (N > 0) {
         SSG_PROF_BEGIN(ctx, "k_apply_lut");
         k_apply_lut<<<gridFor((N + 3) / 4, 256), 256, 0, ctx->stream>>>(segDev, N, lut);
+        SSG_LAUNCHED(ctx);
+    }
+    if (sizeOutDev) {
+        SSG_PROF_BEGIN(ctx, "k_compact_sizes");
+        k_compact_sizes<<<gridFor(len, 256), 256, 0, ctx->stream>>>(sizeDev, lut, len, minSegId, sizeOutDev);
         SSG_LAUNCHED(ctx);
     }
     SSG_TRY(ssg_fetch_counters(ctx));
