@@ -92,6 +92,20 @@ class TileTable(object):
         sel = numpy.flatnonzero(self.flags & _lib.SEG_INTRIM)
         return int(sel[-1]) if len(sel) else 0
 
+    def prepare(self):
+        """Everything of the tile's lut that does not depend on the id offset, so that it can be
+        worked out as soon as the tables exist (while other tiles are still being segmented):
+        (rank where numbered else 0, 1 where numbered else 0, positions of the crossing segments)"""
+        if getattr(self, '_prepared', None) is None:
+            numbered = ((self.flags & _lib.SEG_NUMBERED) != 0)
+            rel = numpy.where(numbered, self.rank, numpy.uint32(0)).astype(numpy.uint32)
+            crossing = numpy.flatnonzero((self.flags & KEY_FLAGS) != 0)
+            self._prepared = (rel, numbered.astype(numpy.uint32), crossing)
+            self.crossingInTrim = crossing[(self.flags[crossing] & _lib.SEG_INTRIM) != 0]
+            self.cachedMaxRankInTrim = self.maxRankInTrim
+            self.pairs()
+        return self._prepared
+
     def pairs(self):
         """(isLeft, segment, neighbour label, count) of the votes, decoded once."""
         if self._split is None:
@@ -187,9 +201,9 @@ class LazyResolver(object):
                 lut = numpy.arange(tb.maxId + 1, dtype=numpy.uint32) + off
                 lut[0] = 0
             else:
-                lut = numpy.where((tb.flags & _lib.SEG_NUMBERED) != 0, tb.rank + off, numpy.uint32(0))
-                lut = lut.astype(numpy.uint32)
-                lut[(tb.flags & KEY_FLAGS) != 0] = self.UNKNOWN
+                (rel, isNumbered, crossing) = tb.prepare()
+                lut = rel + isNumbered * off
+                lut[crossing] = self.UNKNOWN
             self.luts[cr] = lut
         return self.luts[cr]
 
@@ -271,11 +285,21 @@ class LazyResolver(object):
             (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
             lut[k] = mode.astype(numpy.uint32)
 
-    def fullLut(self, cr):
+    def settle(self, cr):
+        """work on every open entry of own tile cr; True when none is left open"""
         lut = self._lutOf(cr)
-        unknown = numpy.flatnonzero(lut == self.UNKNOWN)
+        if self.simple:
+            return True
+        crossing = self.tables[cr].prepare()[2]
+        unknown = crossing[lut[crossing] == self.UNKNOWN]
         if len(unknown) > 0:
             self._resolveCrossing(cr, lut, unknown)
+            return not (lut[unknown] == self.UNKNOWN).any()
+        return True
+
+    def fullLut(self, cr):
+        self.settle(cr)
+        lut = self._lutOf(cr)
         return numpy.where(lut == self.UNKNOWN, 0, lut).astype(numpy.uint32)
 
 
@@ -517,7 +541,7 @@ class ShardedStitch(object):
         mineInts = []
         for cr in self.mine:
             tb = tables[cr]
-            step = tb.maxLabelInTrim if self.simple else tb.maxRankInTrim
+            step = tb.maxLabelInTrim if self.simple else (tb.prepare() and tb.cachedMaxRankInTrim)
             mineInts += [cr[0], cr[1], step]
         steps = {}
         for vals in comm.allgatherArray(numpy.array(mineInts, dtype=numpy.int64)):
@@ -543,7 +567,7 @@ class ShardedStitch(object):
         for _round in range(len(self.order) + 3):
             resolver.requests = {}
             for cr in self.mine:          # (entries settled in an earlier round are kept)
-                luts[cr] = resolver.fullLut(cr)
+                resolver.settle(cr)
             req = []
             for (cr, parts) in sorted(resolver.requests.items()):
                 labels = numpy.unique(numpy.concatenate(parts))
@@ -570,11 +594,19 @@ class ShardedStitch(object):
                     o += 3 + 2 * n
         else:
             raise RuntimeError('sharded stitch: look-ups across ranks did not settle')
+        for cr in self.mine:
+            luts[cr] = resolver.luts[cr]          # nothing is open any more
         # the check of the hypothesis
         ok = 1
         for cr in self.mine:
-            inTrim = (tables[cr].flags & _lib.SEG_INTRIM) != 0
-            trimmedMax = int(luts[cr][inTrim].max()) if inTrim.any() else 0
+            tb = tables[cr]
+            if self.simple:
+                trimmedMax = offsets[cr] + tb.maxLabelInTrim if tb.maxLabelInTrim else 0
+            else:
+                tb.prepare()
+                trimmedMax = offsets[cr] + tb.cachedMaxRankInTrim if tb.cachedMaxRankInTrim else 0
+                if len(tb.crossingInTrim):
+                    trimmedMax = max(trimmedMax, int(luts[cr][tb.crossingInTrim].max()))
             if max(offsets[cr], trimmedMax) != offsets[cr] + steps[cr] or self.forceSequential:
                 ok = 0
         if min(int(v[0]) for v in comm.allgatherArray(numpy.array([ok], dtype=numpy.int64))) == 0:

@@ -961,6 +961,7 @@ class TiledSegmenter(object):
                     if all(nb is None or stitch.owner[nb] == comm.rank for nb in (up, left)):
                         early[cr] = ops.tables(cr, None if (up is None or self.simple) else 'local',
                             None if (left is None or self.simple) else 'local')
+                        early[cr].prepare()      # the offset-independent part of its lut, too
                 for th in workers:
                     th.join()
             with self.timings.interval('stitchtiles'):
