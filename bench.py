@@ -76,6 +76,18 @@ def algorithmic_bytes_per_pixel(kernel, nB):
     return table.get(kernel)
 
 
+# DRAM bytes per pixel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture on
+# a 4096 x 4096 x 4 tile, profiles/r1_tile4096_ncu_full.md, divided by the tile's pixels): scaled by
+# the pixels one launch processes it gives `roofline.traffic`
+NCU_DRAM_BYTES_PER_PIXEL = {
+    'k_small_persistent': (130.1e6 + 40.0e6) / 4096 ** 2,
+    'k_assign': (134.5e6 + 40.9e6) / 4096 ** 2,
+    'k_ccl_local': (67.2e6 + 24.8e6) / 4096 ** 2,
+    'k_band_sums': (220.0e6 + 9.5e6) / 4096 ** 2,
+    'k_gather_ids': (122.8e6 + 31.9e6) / 4096 ** 2,
+}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -456,6 +468,10 @@ def run_ours(args, wl):
             roof['achieved'] = bytesPerLaunch / (avgMs / 1e3) / 1e9
             roof['frac'] = roof['achieved'] / peak
             roof['bytes_per_pixel'] = bpp
+            if domName in NCU_DRAM_BYTES_PER_PIXEL:
+                roof['traffic'] = NCU_DRAM_BYTES_PER_PIXEL[domName] * tilePixels / max(1.0, launchesPerStep)
+                roof['traffic_source'] = ('ncu --set full on a 4096x4096x4 tile (profiles/r1_tile4096_ncu_full.md): '
+                    '%.1f DRAM bytes per pixel, scaled to the mean tile of a launch' % NCU_DRAM_BYTES_PER_PIXEL[domName])
             roof['avg_launch_ms'] = avgMs
             roof['launches_per_step'] = launchesPerStep
             roof['share_of_step'] = domMs / msProfiled
