@@ -631,6 +631,7 @@ __device__ void phase_find(const SmallState &st, unsigned t, const CandSource &s
     const int64_t warpId = gtid >> 5, nWarps = gsize >> 5;
     const int nB = st.nB;
     const unsigned nextCap = 2u * st.cap;
+    const bool eager = nCand < 4096u;
     unsigned long long *ctrF = st.ctr + set * SF_COUNT;
     unsigned *targets = st.targets[set], *nextList = st.nextList[set];
 
@@ -640,18 +641,25 @@ __device__ void phase_find(const SmallState &st, unsigned t, const CandSource &s
         unsigned long long bestKey = ~0ull;
         unsigned bestU = 0;
         unsigned s = 0;
+        // everything that hangs on the candidate's id is requested at once
+        unsigned o0 = 0, n0 = 0, nx0 = SSG_NIL;
+        float ms[NBMAX];
         if (active) {
             s = src.at((unsigned)c);
-            active = st.segSize[s] == t;      // a listed segment may have grown since
+            const unsigned sz = st.segSize[s];
+            o0 = st.sliceOff[s]; n0 = st.sliceLen[s]; nx0 = st.nextChunk[s];
+#pragma unroll
+            for (int b = 0; b < NBMAX; b++) ms[b] = b < nB ? st.fsum[(size_t)s * nB + b] : 0.0f;
+            active = sz == t;      // a listed segment may have grown since
         }
         if (active) {
-            float ms[NBMAX];
 #pragma unroll
             for (int b = 0; b < NBMAX; b++)
-                if (b < nB) ms[b] = seg_mean(st.fsum[(size_t)s * nB + b], t);
+                if (b < nB) ms[b] = seg_mean(ms[b], t);
             unsigned posBase = 0;
-            for (unsigned ch = s; ch != SSG_NIL; ch = st.nextChunk[ch]) {
-                const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
+            for (unsigned ch = s, o = o0, n = n0, nx = nx0; ch != SSG_NIL;
+                 ch = nx, o = ch != SSG_NIL ? st.sliceOff[ch] : 0u, n = ch != SSG_NIL ? st.sliceLen[ch] : 0u,
+                 nx = ch != SSG_NIL ? st.nextChunk[ch] : SSG_NIL) {
                 for (unsigned i = sub; i < n; i += G) {
                     const unsigned p = st.pix[o + i];
                     const unsigned k = posBase + i;
@@ -684,10 +692,14 @@ __device__ void phase_find(const SmallState &st, unsigned t, const CandSource &s
                         float fs[BATCH][NBMAX];
 #pragma unroll
                         for (int e = 0; e < BATCH; e++) {
-                            ok[q0 + e] = ok[q0 + e] && su[q0 + e] > t;     // strictly larger, shepseg.py:1052
+                            // with few candidates the phase waits for latency, not bandwidth: then
+                            // the sums are requested together with the sizes, needed or not
+                            const bool larger = su[q0 + e] > t;            // strictly larger, shepseg.py:1052
+                            const bool fetch = ok[q0 + e] && (eager || larger);
 #pragma unroll
                             for (int b = 0; b < NBMAX; b++)
-                                fs[e][b] = (ok[q0 + e] && b < nB) ? st.fsum[(size_t)nu[q0 + e] * nB + b] : 0.0f;
+                                fs[e][b] = (fetch && b < nB) ? st.fsum[(size_t)nu[q0 + e] * nB + b] : 0.0f;
+                            ok[q0 + e] = ok[q0 + e] && larger;
                         }
 #pragma unroll
                         for (int e = 0; e < BATCH; e++) {
@@ -787,7 +799,10 @@ __device__ void phase_relabel(const SmallState &st, unsigned t, const CandSource
 // shepseg.py:1099-1123).  Only a target that is still small afterwards will have its list walked
 // again; it gets a fresh contiguous slice from the arena (a later find then reads one slice, not
 // a chain of them).  If the arena is exhausted the slices are chained instead.
+// One thread per target, and what it waits for is memory: everything that hangs on the target's id
+// is requested at once, everything that hangs on a source's id while the pending list is walked.
 #define APPLY_SORT_MAX 24
+template <int NBMAX>
 __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *targets,
                             unsigned long long t0, unsigned nT, int64_t gtid, int64_t gsize)
 {
@@ -795,17 +810,30 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
     unsigned long long merged = 0;
     for (int64_t i = gtid; i < (int64_t)nT; i += gsize) {
         const unsigned u = targets[(t0 + i) % st.cap];
-        unsigned ids[APPLY_SORT_MAX];
+        unsigned s = st.pendHead[u];
+        const unsigned oldSize = st.segSize[u];
+        const unsigned uOff = st.sliceOff[u], uLen = st.sliceLen[u], uNext = st.nextChunk[u];
+        float fu[NBMAX];
+#pragma unroll
+        for (int b = 0; b < NBMAX; b++) fu[b] = b < nB ? st.fsum[(size_t)u * nB + b] : 0.0f;
+
+        unsigned ids[APPLY_SORT_MAX], sOff[APPLY_SORT_MAX], sLen[APPLY_SORT_MAX], sNxt[APPLY_SORT_MAX];
         unsigned k = 0;
-        for (unsigned s = st.pendHead[u]; s != 0; s = st.pendNext[s]) {
+        while (s != 0) {
+            const unsigned nxt = st.pendNext[s];
             if (k < APPLY_SORT_MAX) {
+                const unsigned o = st.sliceOff[s], l = st.sliceLen[s], n = st.nextChunk[s];
                 unsigned j = k;
-                while (j > 0 && ids[j - 1] > s) { ids[j] = ids[j - 1]; j--; }
-                ids[j] = s;
+                while (j > 0 && ids[j - 1] > s) {
+                    ids[j] = ids[j - 1]; sOff[j] = sOff[j - 1]; sLen[j] = sLen[j - 1]; sNxt[j] = sNxt[j - 1];
+                    j--;
+                }
+                ids[j] = s; sOff[j] = o; sLen[j] = l; sNxt[j] = n;
             }
             k++;
+            s = nxt;
         }
-        const unsigned oldSize = st.segSize[u];
+        const bool sorted = k <= APPLY_SORT_MAX;
         const unsigned newSize = oldSize + k * t;      // every source has exactly t pixels
         const bool keepList = newSize < (unsigned)st.minSegSize;   // then u was small all along
         unsigned dst = SSG_NIL, w = 0;
@@ -813,7 +841,8 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
             const unsigned long long a = atomicAdd(&st.ctr[SC_ARENA], (unsigned long long)newSize);
             if (a + newSize <= st.arenaCap) {
                 dst = st.arenaBase + (unsigned)a;
-                for (unsigned ch = u; ch != SSG_NIL; ch = st.nextChunk[ch]) {
+                for (unsigned q = 0; q < uLen; q++) st.pix[dst + w++] = st.pix[uOff + q];
+                for (unsigned ch = uNext; ch != SSG_NIL; ch = st.nextChunk[ch]) {
                     const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
                     for (unsigned q = 0; q < n; q++) st.pix[dst + w++] = st.pix[o + q];
                 }
@@ -821,33 +850,35 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
         }
         unsigned last = 0;   // ids are >= 1
         for (unsigned m = 0; m < k; m++) {
-            unsigned s;
-            if (k <= APPLY_SORT_MAX) s = ids[m];
+            unsigned sm, o, l, n;
+            if (sorted) { sm = ids[m]; o = sOff[m]; l = sLen[m]; n = sNxt[m]; }
             else {           // long lists: smallest pending source with id > last
-                s = SSG_NIL;
+                sm = SSG_NIL;
                 for (unsigned q = st.pendHead[u]; q != 0; q = st.pendNext[q])
-                    if (q > last && q < s) s = q;
+                    if (q > last && q < sm) sm = q;
+                o = st.sliceOff[sm]; l = st.sliceLen[sm]; n = st.nextChunk[sm];
             }
-            for (int b = 0; b < nB; b++) {
-                float *tu = &st.fsum[(size_t)u * nB + b];
-                float *ts = &st.fsum[(size_t)s * nB + b];
-                *tu = __fadd_rn(*tu, *ts);
-                *ts = 0.0f;
-            }
-            st.segSize[s] = 0;
+#pragma unroll
+            for (int b = 0; b < NBMAX; b++)
+                if (b < nB) fu[b] = __fadd_rn(fu[b], st.fsum[(size_t)sm * nB + b]);
+            st.segSize[sm] = 0;
             if (keepList) {
                 if (dst != SSG_NIL) {
-                    for (unsigned ch = s; ch != SSG_NIL; ch = st.nextChunk[ch]) {
-                        const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
-                        for (unsigned q = 0; q < n; q++) st.pix[dst + w++] = st.pix[o + q];
+                    for (unsigned q = 0; q < l; q++) st.pix[dst + w++] = st.pix[o + q];
+                    for (unsigned ch = n; ch != SSG_NIL; ch = st.nextChunk[ch]) {
+                        const unsigned o2 = st.sliceOff[ch], n2 = st.sliceLen[ch];
+                        for (unsigned q = 0; q < n2; q++) st.pix[dst + w++] = st.pix[o2 + q];
                     }
                 } else {
-                    st.nextChunk[st.tailChunk[u]] = s;
-                    st.tailChunk[u] = st.tailChunk[s];
+                    st.nextChunk[st.tailChunk[u]] = sm;
+                    st.tailChunk[u] = st.tailChunk[sm];
                 }
             }
-            last = s;
+            last = sm;
         }
+#pragma unroll
+        for (int b = 0; b < NBMAX; b++)
+            if (b < nB) st.fsum[(size_t)u * nB + b] = fu[b];
         st.segSize[u] = newSize;
         st.pendHead[u] = 0;
         merged += k;
@@ -925,7 +956,7 @@ k_small_persistent(SmallState st)
             passes++;
             if (nT == 0) break;      // nothing merged: the count of this size is unchanged
             phase_relabel(st, (unsigned)t, src, gtid, gsize);
-            phase_apply(st, (unsigned)t, st.targets[set], tg0, nT, gtid, gsize);
+            phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], tg0, nT, gtid, gsize);
             DBG_TICK(2);
             small_barrier(st, phase, set, cur);    // (the find counters did not move)
             DBG_TICK(3);
