@@ -775,7 +775,11 @@ __device__ void phase_select(const SmallState &st, unsigned size, int set, int64
     }
 }
 
-// seg[pixels of source] = target (first half of doMerge, shepseg.py:1107-1110)
+// seg[pixels of source] = target (first half of doMerge, shepseg.py:1107-1110).
+// Runs concurrently with phase_apply on other blocks: it reads the sources' slices and pixel
+// lists, which apply only reads too (a source is never a target in the same pass); the one thing
+// apply may change under its feet is the last link of a source's chain when slices are being
+// chained, and following that link only relabels the next source of the SAME target.
 __device__ void phase_relabel(const SmallState &st, unsigned t, const CandSource &src,
                               int64_t gtid, int64_t gsize)
 {
@@ -802,6 +806,20 @@ __device__ void phase_relabel(const SmallState &st, unsigned t, const CandSource
 // One thread per target, and what it waits for is memory: everything that hangs on the target's id
 // is requested at once, everything that hangs on a source's id while the pending list is walked.
 #define APPLY_SORT_MAX 24
+// n pixels from pix[src..] to pix[dst..], eight loads in flight at a time (a plain copy loop
+// issues load, store, load, store and waits a memory latency per pixel)
+__device__ __forceinline__ void copy_pixels(unsigned *pix, unsigned dst, unsigned src, unsigned n)
+{
+    for (unsigned q = 0; q < n; q += 8) {
+        unsigned v[8];
+#pragma unroll
+        for (unsigned i = 0; i < 8; i++) v[i] = (q + i < n) ? pix[src + q + i] : 0u;
+#pragma unroll
+        for (unsigned i = 0; i < 8; i++)
+            if (q + i < n) pix[dst + q + i] = v[i];
+    }
+}
+
 template <int NBMAX>
 __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *targets,
                             unsigned long long t0, unsigned nT, int64_t gtid, int64_t gsize)
@@ -841,10 +859,12 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
             const unsigned long long a = atomicAdd(&st.ctr[SC_ARENA], (unsigned long long)newSize);
             if (a + newSize <= st.arenaCap) {
                 dst = st.arenaBase + (unsigned)a;
-                for (unsigned q = 0; q < uLen; q++) st.pix[dst + w++] = st.pix[uOff + q];
+                copy_pixels(st.pix, dst, uOff, uLen);
+                w = uLen;
                 for (unsigned ch = uNext; ch != SSG_NIL; ch = st.nextChunk[ch]) {
                     const unsigned o = st.sliceOff[ch], n = st.sliceLen[ch];
-                    for (unsigned q = 0; q < n; q++) st.pix[dst + w++] = st.pix[o + q];
+                    copy_pixels(st.pix, dst + w, o, n);
+                    w += n;
                 }
             }
         }
@@ -864,10 +884,12 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
             st.segSize[sm] = 0;
             if (keepList) {
                 if (dst != SSG_NIL) {
-                    for (unsigned q = 0; q < l; q++) st.pix[dst + w++] = st.pix[o + q];
+                    copy_pixels(st.pix, dst + w, o, l);
+                    w += l;
                     for (unsigned ch = n; ch != SSG_NIL; ch = st.nextChunk[ch]) {
                         const unsigned o2 = st.sliceOff[ch], n2 = st.sliceLen[ch];
-                        for (unsigned q = 0; q < n2; q++) st.pix[dst + w++] = st.pix[o2 + q];
+                        copy_pixels(st.pix, dst + w, o2, n2);
+                        w += n2;
                     }
                 } else {
                     st.nextChunk[st.tailChunk[u]] = sm;
@@ -955,8 +977,16 @@ k_small_persistent(SmallState st)
             numPasses++;
             passes++;
             if (nT == 0) break;      // nothing merged: the count of this size is unchanged
-            phase_relabel(st, (unsigned)t, src, gtid, gsize);
-            phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], tg0, nT, gtid, gsize);
+            // the two halves of doMerge are independent (see phase_relabel): half of the blocks
+            // take each, so a pass waits for the longer of the two chains instead of their sum
+            if (gridDim.x >= 2) {
+                const int64_t half = (int64_t)(gridDim.x / 2) * blockDim.x;
+                if (gtid < half) phase_relabel(st, (unsigned)t, src, gtid, half);
+                else phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], tg0, nT, gtid - half, gsize - half);
+            } else {
+                phase_relabel(st, (unsigned)t, src, gtid, gsize);
+                phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], tg0, nT, gtid, gsize);
+            }
             DBG_TICK(2);
             small_barrier(st, phase, set, cur);    // (the find counters did not move)
             DBG_TICK(3);
