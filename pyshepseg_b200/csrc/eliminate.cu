@@ -419,8 +419,8 @@ static int build_spectra_t(ssg_ctx *ctx, const T *img, int nB, int64_t N, const 
 // scan, the histogram of those sizes, and the totals
 __global__ void __launch_bounds__(256)
 k_small_census(const unsigned *__restrict__ segSize, int64_t len, unsigned minSegSize,
-               unsigned *cnt /* len + 1 */, unsigned *sizeHist /* minSegSize + 1 */,
-               unsigned long long *counters)
+               unsigned *cnt /* len + 1 */, unsigned *isSmall /* len + 1 */,
+               unsigned *sizeHist /* minSegSize + 1 */, unsigned long long *counters)
 {
     extern __shared__ unsigned hist[];
     for (unsigned i = threadIdx.x; i < minSegSize; i += blockDim.x) hist[i] = 0;
@@ -431,7 +431,7 @@ k_small_census(const unsigned *__restrict__ segSize, int64_t len, unsigned minSe
         const unsigned z = segSize[s];
         if (z > 0 && z < minSegSize) c = z;
     }
-    if (s <= len) cnt[s] = c;
+    if (s <= len) { cnt[s] = c; isSmall[s] = c ? 1u : 0u; }
     if (c) atomicAdd(&hist[c], 1u);
     const unsigned m = __ballot_sync(0xffffffffu, c != 0);
     const unsigned pixTot = __reduce_add_sync(0xffffffffu, c);
@@ -467,35 +467,49 @@ k_bucket_fill(const unsigned *__restrict__ segSize, int64_t len, unsigned minSeg
     if (z) bucketList[base[z] + myRank] = (unsigned)s;
 }
 
+// per-segment state of the passes.  A small segment's pixel list lives either in a region of its
+// own of minSegSize-1 entries (regionCap != 0: the list only ever grows by appending, and cannot
+// outgrow the region while the segment is still small) or, when that would take too much memory,
+// in a slice of a packed array (merged lists are then rewritten into an arena, see phase_apply).
 __global__ void __launch_bounds__(256)
-k_list_fill(const unsigned *__restrict__ seg, int64_t N, const unsigned *__restrict__ off,
-            unsigned *fill, unsigned *pix)
+k_list_init(const unsigned *__restrict__ off, const unsigned *__restrict__ smallRank,
+            const unsigned *__restrict__ segSize, int64_t len, unsigned minSegSize, unsigned regionCap,
+            unsigned *sliceOff, unsigned *sliceLen, unsigned *nextChunk, unsigned *tailChunk,
+            unsigned *mergeTo, unsigned *pendHead, unsigned *fill)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    const unsigned n = off[s + 1] - off[s];
+    sliceOff[s] = regionCap ? smallRank[s] * regionCap : off[s];
+    sliceLen[s] = n;
+    nextChunk[s] = SSG_NIL;
+    tailChunk[s] = (unsigned)s;
+    mergeTo[s] = 0;
+    pendHead[s] = 0;
+    fill[s] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_list_fill(const unsigned *__restrict__ seg, int64_t N, const unsigned *__restrict__ sliceOff,
+            const unsigned *__restrict__ sliceLen, unsigned *fill, unsigned *pix)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const unsigned s = seg[p];
     if (s == 0) return;
-    const unsigned o = off[s], n = off[s + 1] - o;
-    if (n == 0) return;
+    if (sliceLen[s] == 0) return;
     const unsigned slot = atomicAdd(&fill[s], 1u);
-    pix[o + slot] = (unsigned)p;
+    pix[sliceOff[s] + slot] = (unsigned)p;
 }
 
 // slots were claimed in arbitrary order: put every list back into raster order
 __global__ void __launch_bounds__(128)
-k_list_sort(const unsigned *__restrict__ off, int64_t len, unsigned *pix, unsigned *sliceOff,
-            unsigned *sliceLen, unsigned *nextChunk, unsigned *tailChunk, unsigned *mergeTo,
-            unsigned *pendHead)
+k_list_sort(const unsigned *__restrict__ sliceOff, const unsigned *__restrict__ sliceLen, int64_t len,
+            unsigned *pix)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= len) return;
-    sliceOff[s] = off[s];
-    sliceLen[s] = off[s + 1] - off[s];
-    nextChunk[s] = SSG_NIL;
-    tailChunk[s] = (unsigned)s;
-    mergeTo[s] = 0;
-    pendHead[s] = 0;
-    const unsigned o = off[s], n = off[s + 1] - o;
+    const unsigned o = sliceOff[s], n = sliceLen[s];
     for (unsigned i = 1; i < n; i++) {
         unsigned v = pix[o + i];
         unsigned j = i;
@@ -549,6 +563,7 @@ struct SmallState {
     unsigned long long *dbg;       // optional: cycles per phase kind, written by thread 0
     unsigned cap;                  // number of initially small segments
     unsigned arenaBase, arenaCap;  // arena = pix[arenaBase, arenaBase + arenaCap)
+    unsigned regionCap;            // != 0: every small segment owns pix[sliceOff, sliceOff + regionCap)
     int nB;
     int64_t nRows, nCols;
     int four;
@@ -821,7 +836,7 @@ __device__ __forceinline__ void copy_pixels(unsigned *pix, unsigned dst, unsigne
 }
 
 template <int NBMAX>
-__device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *targets,
+__device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *targets, int set,
                             unsigned long long t0, unsigned nT, int64_t gtid, int64_t gsize)
 {
     const int nB = st.nB;
@@ -855,7 +870,10 @@ __device__ void phase_apply(const SmallState &st, unsigned t, const unsigned *ta
         const unsigned newSize = oldSize + k * t;      // every source has exactly t pixels
         const bool keepList = newSize < (unsigned)st.minSegSize;   // then u was small all along
         unsigned dst = SSG_NIL, w = 0;
-        if (keepList) {
+        if (keepList && st.regionCap) {
+            dst = uOff;        // the sources are appended in place
+            w = uLen;
+        } else if (keepList) {
             const unsigned long long a = atomicAdd(&st.ctr[SC_ARENA], (unsigned long long)newSize);
             if (a + newSize <= st.arenaCap) {
                 dst = st.arenaBase + (unsigned)a;
@@ -982,10 +1000,10 @@ k_small_persistent(SmallState st)
             if (gridDim.x >= 2) {
                 const int64_t half = (int64_t)(gridDim.x / 2) * blockDim.x;
                 if (gtid < half) phase_relabel(st, (unsigned)t, src, gtid, half);
-                else phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], tg0, nT, gtid - half, gsize - half);
+                else phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], set, tg0, nT, gtid - half, gsize - half);
             } else {
                 phase_relabel(st, (unsigned)t, src, gtid, gsize);
-                phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], tg0, nT, gtid, gsize);
+                phase_apply<NBMAX>(st, (unsigned)t, st.targets[set], set, tg0, nT, gtid, gsize);
             }
             DBG_TICK(2);
             small_barrier(st, phase, set, cur);    // (the find counters did not move)
@@ -1044,9 +1062,9 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses, i
         for (int i = 0; i < 6; i++)
             fprintf(stderr, "  small phase %-14s n=%5llu  %8.1f us total  %6.2f us each\n", names[i], d[6 + i],
                     d[i] / 1965.0, d[6 + i] ? d[i] / 1965.0 / d[6 + i] : 0.0);
-        fprintf(stderr, "  small: %llu small segments, %llu arena pixels of %u, %llu grown\n",
-                (unsigned long long)st.cap, (unsigned long long)host[SC_ARENA], st.arenaCap,
-                (unsigned long long)host[SC_GROWN]);
+        fprintf(stderr, "  small: %llu small segments, lists in %s, %llu arena pixels of %u\n",
+                (unsigned long long)st.cap, st.regionCap ? "regions" : "packed slices + arena",
+                (unsigned long long)host[SC_ARENA], st.arenaCap);
         unsigned long long pt[240];
         SSG_CUDA(ctx, cudaMemcpy(pt, st.dbg, sizeof(pt), cudaMemcpyDeviceToHost));
         fprintf(stderr, "  small: us per target size (last list length):");
@@ -1073,17 +1091,19 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
 
     SSG_TRY(build_spectra_t<T>(ctx, img, nB, N, seg, segSize, len));
 
-    // census of the small segments: listed sizes (-> slice offsets) and the size histogram
-    // (-> buckets); both scans share one scratch array: [off: len+1][hist: m+1][start: m+1][fill: m+1]
+    // census of the small segments: listed sizes (-> slice offsets), 0/1 flags (-> rank among the
+    // small segments) and the size histogram (-> buckets); the three scans share one scratch
+    // array: [off: len+1][rank: len+1][hist: m+1][start: m+1][fill: m+1]
     const size_t m1 = (size_t)minSegSize + 1;
-    SSG_TRY(ssg_reserve(ctx, ctx->listOff, ((size_t)(len + 1) + 3 * m1) * sizeof(unsigned)));
+    SSG_TRY(ssg_reserve(ctx, ctx->listOff, (2 * (size_t)(len + 1) + 3 * m1) * sizeof(unsigned)));
     unsigned *off = bufp<unsigned>(ctx->listOff);
-    unsigned *sizeHist = off + (len + 1), *bucketStart = sizeHist + m1, *bucketFill = bucketStart + m1;
+    unsigned *smallRank = off + (len + 1);
+    unsigned *sizeHist = smallRank + (len + 1), *bucketStart = sizeHist + m1, *bucketFill = bucketStart + m1;
     SSG_CUDA(ctx, cudaMemsetAsync(sizeHist, 0, 3 * m1 * sizeof(unsigned), ctx->stream));
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_SMALLSEG, 0, 2 * sizeof(unsigned long long), ctx->stream));
     SSG_PROF_BEGIN(ctx, "k_small_census");
     k_small_census<<<gridFor(len + 1, 256), 256, (size_t)minSegSize * sizeof(unsigned), ctx->stream>>>(
-        segSize, len, (unsigned)minSegSize, off, sizeHist, counters);
+        segSize, len, (unsigned)minSegSize, off, smallRank, sizeHist, counters);
     SSG_LAUNCHED(ctx);
     size_t tmpBytes = 0, tmpBytes2 = 0;
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, off, off, (int)(len + 1), ctx->stream));
@@ -1093,6 +1113,9 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, off, off, (int)(len + 1), ctx->stream));
     SSG_LAUNCHED(ctx);
     SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
+    SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, smallRank, smallRank, (int)(len + 1), ctx->stream));
+    SSG_LAUNCHED(ctx);
+    SSG_PROF_BEGIN(ctx, "cub_DeviceScan_ExclusiveSum");
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes2, sizeHist, bucketStart, (int)m1, ctx->stream));
     SSG_LAUNCHED(ctx);
     SSG_TRY(ssg_fetch_counters(ctx));
@@ -1100,28 +1123,40 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     const size_t numSmallPix = (size_t)ctx->hostCounters[C_NUM_SMALLPIX];
     if (numSmall == 0) return SSG_OK;   // nothing can be a candidate, now or later
 
-    // the arena holds the rewritten lists of merged segments; 2x the listed pixels covers the
-    // imagery seen so far several times over, and running out only costs speed (chained slices)
-    size_t arenaCap = 2 * numSmallPix;
-    if (const char *e = getenv("SSG_SMALL_ARENA_PCT")) arenaCap = numSmallPix * (size_t)atoi(e) / 100;
-    if (numSmallPix + arenaCap > 0xFFFFFFF0ull) arenaCap = 0xFFFFFFF0ull - numSmallPix;
+    // Pixel lists.  By default every small segment gets a region of minSegSize-1 entries of its
+    // own: a list only ever grows by appending the lists of merged sources, and it cannot outgrow
+    // the region while its segment is still below minSegSize -- so merging never moves the
+    // target's pixels, needs no allocation and lists never fragment.  That takes
+    // (minSegSize-1) * 4 bytes per small segment (170 MB for a 7908^2 tile at minSegSize=50); if
+    // it would exceed the limit (a very large minSegSize) the lists are packed instead and merged
+    // lists are rewritten into an arena of twice their size, chained when that runs out.
+    size_t regionLimit = (size_t)8 << 30;
+    if (const char *e = getenv("SSG_SMALL_REGION_MB")) regionLimit = (size_t)atoll(e) << 20;
+    const size_t regionEntries = numSmall * (size_t)(minSegSize - 1);
+    const bool regions = regionEntries * sizeof(unsigned) <= regionLimit && regionEntries < 0xFFFFFFF0ull;
+    size_t arenaCap = 0;
+    if (!regions) {
+        arenaCap = 2 * numSmallPix;
+        if (const char *e = getenv("SSG_SMALL_ARENA_PCT")) arenaCap = numSmallPix * (size_t)atoi(e) / 100;
+        if (numSmallPix + arenaCap > 0xFFFFFFF0ull) arenaCap = 0xFFFFFFF0ull - numSmallPix;
+    }
+    const size_t pixEntries = regions ? regionEntries : numSmallPix + arenaCap;
     const size_t tbl = (size_t)len * sizeof(unsigned);
-    SSG_TRY(ssg_reserve(ctx, ctx->aux0, (numSmallPix + arenaCap) * sizeof(unsigned)));   // pixel store
+    SSG_TRY(ssg_reserve(ctx, ctx->aux0, pixEntries * sizeof(unsigned)));                 // pixel store
     SSG_TRY(ssg_reserve(ctx, ctx->aux1, 2 * tbl));                                       // slices
     SSG_TRY(ssg_reserve(ctx, ctx->nextChunk, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->tailChunk, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->mergeTo, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->pendHead, tbl));
     SSG_TRY(ssg_reserve(ctx, ctx->pendNext, tbl));
-    // lists of the passes: grown log (u64), bucket, 2 target rings, 2 next rings (2x), 2 selections
-    SSG_TRY(ssg_reserve(ctx, ctx->candList, numSmall * 11 * sizeof(unsigned) + sizeof(SmallBarrier) +
+    // lists of the passes: grown log (2 x u64), bucket, 2 target rings, 2 next rings (2x), 2 selections
+    SSG_TRY(ssg_reserve(ctx, ctx->candList, numSmall * 13 * sizeof(unsigned) + sizeof(SmallBarrier) +
                                             SC_COUNT * sizeof(unsigned long long) + 64));
     unsigned *pix = bufp<unsigned>(ctx->aux0);
     unsigned *sliceOff = bufp<unsigned>(ctx->aux1), *sliceLen = sliceOff + len;
     unsigned *fill = bufp<unsigned>(ctx->pendNext);   // free until the passes start
-    SSG_CUDA(ctx, cudaMemsetAsync(fill, 0, tbl, ctx->stream));
     unsigned long long *grownLog = bufp<unsigned long long>(ctx->candList);
-    unsigned *bucketList = reinterpret_cast<unsigned *>(grownLog + numSmall);
+    unsigned *bucketList = reinterpret_cast<unsigned *>(grownLog + 2 * numSmall);
     unsigned *lists = bucketList + numSmall;
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>(
         ((uintptr_t)(lists + 8 * numSmall) + 15) & ~(uintptr_t)15);
@@ -1131,13 +1166,16 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     k_bucket_fill<<<gridFor(len, 256), 256, 2 * (size_t)minSegSize * sizeof(unsigned), ctx->stream>>>(
         segSize, len, (unsigned)minSegSize, bucketStart, bucketFill, bucketList);
     SSG_LAUNCHED(ctx);
+    SSG_PROF_BEGIN(ctx, "k_list_init");
+    k_list_init<<<gridFor(len, 256), 256, 0, ctx->stream>>>(off, smallRank, segSize, len, (unsigned)minSegSize,
+        regions ? (unsigned)(minSegSize - 1) : 0u, sliceOff, sliceLen, bufp<unsigned>(ctx->nextChunk),
+        bufp<unsigned>(ctx->tailChunk), bufp<unsigned>(ctx->mergeTo), bufp<unsigned>(ctx->pendHead), fill);
+    SSG_LAUNCHED(ctx);
     SSG_PROF_BEGIN(ctx, "k_list_fill");
-    k_list_fill<<<gridFor(N, 256), 256, 0, ctx->stream>>>(seg, N, off, fill, pix);
+    k_list_fill<<<gridFor(N, 256), 256, 0, ctx->stream>>>(seg, N, sliceOff, sliceLen, fill, pix);
     SSG_LAUNCHED(ctx);
     SSG_PROF_BEGIN(ctx, "k_list_sort");
-    k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(off, len, pix, sliceOff, sliceLen,
-                                                           bufp<unsigned>(ctx->nextChunk), bufp<unsigned>(ctx->tailChunk),
-                                                           bufp<unsigned>(ctx->mergeTo), bufp<unsigned>(ctx->pendHead));
+    k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(sliceOff, sliceLen, len, pix);
     SSG_LAUNCHED(ctx);
 
     SmallState st;
@@ -1153,6 +1191,7 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     st.grownLog = grownLog;
     st.ctr = ctr; st.bar = bar; st.cap = (unsigned)numSmall;
     st.arenaBase = (unsigned)numSmallPix; st.arenaCap = (unsigned)arenaCap;
+    st.regionCap = regions ? (unsigned)(minSegSize - 1) : 0u;
     st.dbg = nullptr;
     if (getenv("SSG_SMALL_DEBUG")) {   // phase timing of the persistent kernel, to stderr
         SSG_TRY(ssg_reserve(ctx, ctx->targetList, 240 * sizeof(unsigned long long)));

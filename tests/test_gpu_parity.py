@@ -192,21 +192,28 @@ def test_big_values_inexact_sums(shepseg):
     _against_oracle(shepseg, img, 8, 200, None, True, None, 'bigvalues')
 
 
-@pytest.mark.parametrize('env', [('SSG_SMALL_ARENA_PCT', '0'), ('SSG_SMALL_ARENA_PCT', '7'),
-    ('SSG_SMALL_BLOCKS_PER_SM', '1'), ('SSG_SMALL_BLOCKS_PER_SM', '4')],
-    ids=['no_arena_all_chained', 'arena_runs_out_midway', 'one_block_per_sm', 'four_blocks_per_sm'])
+@pytest.mark.parametrize('env', [
+    {'SSG_SMALL_REGION_MB': '0'},
+    {'SSG_SMALL_REGION_MB': '0', 'SSG_SMALL_ARENA_PCT': '0'},
+    {'SSG_SMALL_REGION_MB': '0', 'SSG_SMALL_ARENA_PCT': '7'},
+    {'SSG_SMALL_BLOCKS_PER_SM': '2'},
+    {'SSG_SMALL_THREADS': '128'},
+], ids=['packed_lists_arena', 'packed_lists_all_chained', 'packed_lists_arena_runs_out', 'two_blocks_per_sm',
+    'small_blocks'])
 def test_small_segment_list_storage_and_grid(shepseg, env):
-    """the merged pixel lists are rewritten into an arena while it lasts and chained after that;
-    neither that nor the size of the persistent grid may change a label"""
+    """pixel lists normally live in per-segment regions; when that would take too much memory
+    they are packed, merged lists rewritten into an arena while it lasts and chained after that.
+    Neither the storage nor the shape of the persistent grid may change a label."""
     img = synth.synth_v1(600, 700, 4, seed=10)
     km = goldenutil.Centres(synth.diagonal_centres(img, 40))
     want = oracle.doShepherdSegmentation(img, minSegmentSize=40, kmeansObj=km)
-    os.environ[env[0]] = env[1]
+    os.environ.update(env)
     try:
         got = shepseg.doShepherdSegmentation(img, minSegmentSize=40, kmeansObj=km)
     finally:
-        del os.environ[env[0]]
-    same(got.segimg, want.segimg, '%s=%s' % env)
+        for k in env:
+            del os.environ[k]
+    same(got.segimg, want.segimg, str(env))
     assert got.smallSegmentsEliminated == want.smallSegmentsEliminated
 
 
