@@ -288,7 +288,11 @@ def run_ours(args, wl):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        # a rank that dies must take the job down quickly instead of leaving the others in a
+        # collective for ten minutes
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local),
+            timeout=datetime.timedelta(seconds=240))
 
     # ---- set-up (untimed): the raster in pinned host memory, centres from rank 0 over NCCL ----
     # N = 1: the scene.  N > 1: ONE mosaic of N scenes (weak scaling), its tiles dealt over the

@@ -969,10 +969,14 @@ class TiledSegmenter(object):
                 with self.timings.interval('stitch_applywait'):
                     main.ctx.synchronize()
                 with self.timings.interval('stitch_histogram'):
+                    # Every rank takes the SAME branch and reduces the SAME number of entries:
+                    # which collective runs must not hang on anything rank-local (a rank whose
+                    # tiles carry small ids has a smaller histogram buffer than the others).
                     n = maxSegId + 1
-                    if onDevice and hist.dev is not None and n <= hist.cap:
+                    hist.ensure(main.ctx, n)
+                    if onDevice:
                         # summed over the ranks on the devices into rank 0, which alone holds the
-                        # output's histogram (the other ranks return None for it)
+                        # output's histogram (the other ranks return an empty one)
                         t = torch.empty(n, dtype=torch.int64, device=cudaDev)
                         main.ctx.call('ssg_memcpy_d2d', t.data_ptr(), hist.dev, n * 8)
                         main.ctx.synchronize()
