@@ -378,7 +378,14 @@ def run_ours(args, wl):
         last = None
         for _ in range(steps):
             t0 = time.time()
-            last = stepFn()
+            try:
+                last = stepFn()
+            except BaseException:
+                # a rank that fails must not leave the others waiting in a collective
+                import traceback
+                traceback.print_exc()
+                sys.stderr.flush()
+                os._exit(1)
             exchange_ids(last[1])
             if args.verbose_steps and rank == 0:
                 print('  step %s: %.1f ms' % (getattr(stepFn, '__name__', '?'), (time.time() - t0) * 1e3),

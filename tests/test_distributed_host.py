@@ -93,6 +93,10 @@ def _rank_main(rank, world, port, case, forceSequential, resq):
         (kind, seed, nR, nC, tileSize, overlap, simple) = case
         (ti, allSegs) = make_tiles(kind, seed, nR, nC, tileSize, overlap)
         comm = distributed.TorchComm()
+        if world >= 4:
+            # force the sizes-first gather: the request arrays do not fit the one-shot buffer
+            realGather = comm.allgatherArray
+            comm.allgatherArray = lambda a, quick=64: realGather(a, quick)
         st = distributed.ShardedStitch(ti, overlap, simple, comm)
         st.forceSequential = forceSequential
         # a rank only ever touches the labels of its own tiles (remote strips arrive by message)
@@ -127,6 +131,10 @@ CASES = [
     # maximum), forced
     ('w2_forced_sequential', 2, ('blobby', 14, 260, 300, 96, 32, False), True),
     ('w3_blobby_simple', 3, ('blobby', 15, 260, 300, 96, 32, True), False),
+    # more ranks than tile rows: a rank's upper neighbours belong to two different ranks, ids are
+    # inherited around corners across rank boundaries (several look-up rounds)
+    ('w4_6x6', 4, ('segmented', 16, 420, 430, 96, 32, False), False),
+    ('w8_blobby_7x6', 8, ('blobby', 17, 400, 460, 96, 32, False), False),
 ]
 
 
