@@ -226,7 +226,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    threads = min(cores, 16)
+    threads = min(cores, 64)      # one tile per host thread (the reference's numba stages are single threaded)
     tile = 2048 if args.quick else 4096
     img = make_scene(wl, seed=1)
     centres = scene_centres(wl, img)
@@ -500,7 +500,7 @@ def run_ours(args, wl):
 
         cpu = None
         if args.gpus == 1 and not args.no_cpu_baseline:
-            threads = min(os.cpu_count() or 1, 16)
+            threads = min(os.cpu_count() or 1, 64)
             tile = 2048 if args.quick else 4096
             (p, s) = cpu_reference_sample(wl, img, centres, threads, tile=tile)
             cpu = {'value': p / s / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',

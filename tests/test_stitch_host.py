@@ -144,3 +144,32 @@ def test_three_phase_stitch_random_labels():
     (got, gotMax) = three_phase_stitch(segs, ti, nC, nR, overlap)
     assert gotMax == wantMax
     assert numpy.array_equal(got, want)
+
+
+def test_raster_upload_cells_tile_the_tiles():
+    """the host-to-device upload cuts the raster along every tile edge; the cells of a tile must
+    cover exactly its rectangle, and a cell is sent once however many tiles share it"""
+    for (xs, ys, tileSize, overlap, yoff) in ((2745, 2745, 1024, 256, 0), (5000, 3100, 1024, 256, 0),
+            (4000, 1800, 1024, 256, 768)):
+        ti = tiling.getTilesForFile((xs, ys + yoff), tileSize, overlap)
+        order = sorted(ti.tiles.keys(), key=lambda cr: (cr[1], cr[0]))
+        mine = [cr for cr in order if ti.tiles[cr][1] >= yoff]      # a rank's row band
+        bandRows = max(ti.tiles[cr][1] + ti.tiles[cr][3] for cr in mine) - yoff
+        tiles = [(cr,) + tuple(ti.tiles[cr]) for cr in mine]
+        up = tiling._RasterUploader(None, 0, [1, 2], bandRows, xs, 2, 0, tiles, yoff)
+        sent = numpy.zeros((bandRows, xs), dtype=numpy.int32)
+        done = set()
+        for t in up.tiles:
+            cover = numpy.zeros((bandRows, xs), dtype=bool)
+            for cell in up._cellsOf(t):
+                (x0, y0, x1, y1) = cell
+                assert not cover[y0:y1, x0:x1].any()
+                cover[y0:y1, x0:x1] = True
+                if cell not in done:
+                    done.add(cell)
+                    sent[y0:y1, x0:x1] += 1
+            (k, x, y, w, h) = t
+            want = numpy.zeros((bandRows, xs), dtype=bool)
+            want[y:y + h, x:x + w] = True
+            assert numpy.array_equal(cover, want)
+        assert sent.max() == 1
