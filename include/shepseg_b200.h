@@ -98,6 +98,12 @@ int ssg_eliminate_single_pixels(ssg_ctx *ctx, const void *img, int dtype, int nB
                                 uint32_t *segSize, int64_t len, uint32_t minSegId,
                                 int fourConnected, int64_t *numMoved);
 
+/* shepseg.relabelSegments (shepseg.py:739-777): ids >= minSegId that own no pixel
+ * (segSize == 0) are squeezed out, order preserved; seg is recoded in place, segSize (len
+ * entries) is left as it is, like the reference leaves it.  Every id in seg must be below len. */
+int ssg_relabel_segments(ssg_ctx *ctx, uint32_t *seg, int64_t nPixels, const uint32_t *segSize,
+                         int64_t len, uint32_t minSegId);
+
 /* shepseg.eliminateSmallSegments (shepseg.py:918-1000).  spectralThreshold is
  * maxSpectralDiff**2 evaluated in maxSpectralDiff's own type (float32 product for a
  * numpy.float32, shepseg.py:1060) and widened to double by the caller. */

@@ -75,6 +75,7 @@ SIGNATURES = {
     'ssg_make_seg_size': (_i, [_vp, _vp, _i64, _vp, _i64]),
     'ssg_eliminate_single_pixels': (_i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _i64, _u32, _i,
         _c.POINTER(_i64)]),
+    'ssg_relabel_segments': (_i, [_vp, _vp, _i64, _vp, _i64, _u32]),
     'ssg_eliminate_small_segments': (_i, [_vp, _vp, _vp, _i, _i, _i64, _i64, _u32, _i, _dbl, _i, _u32,
         _c.POINTER(_i64)]),
     'ssg_segment_tile': (_i, [_vp, _vp, _c.POINTER(TileParams), _vp, _c.POINTER(TileResult)]),

@@ -327,6 +327,24 @@ int ssg_eliminate_single_pixels(ssg_ctx *ctx, const void *img, int dtype, int nB
     return SSG_OK;
 }
 
+int ssg_relabel_segments(ssg_ctx *ctx, uint32_t *seg, int64_t nPixels, const uint32_t *segSize, int64_t len,
+                         uint32_t minSegId)
+{
+    CTX_ENTER(ctx);
+    SSG_TRY(ssg_scratch_reset(ctx));
+    if (nPixels < 0 || len < 0 || (!seg && nPixels > 0) || (!segSize && len > 0)) SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument");
+    if (nPixels == 0 || len == 0) return SSG_OK;
+    SSG_TRY(ssg_reserve(ctx, ctx->seg, (size_t)nPixels * sizeof(uint32_t)));
+    SSG_TRY(ssg_reserve(ctx, ctx->segSize, (size_t)len * sizeof(uint32_t)));
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->seg.p, seg, (size_t)nPixels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SSG_CUDA(ctx, cudaMemcpyAsync(ctx->segSize.p, segSize, (size_t)len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t alive = 0;
+    SSG_TRY(ssgk_relabel(ctx, bufp<uint32_t>(ctx->seg), nPixels, bufp<uint32_t>(ctx->segSize), len, minSegId, &alive));
+    SSG_CUDA(ctx, cudaMemcpyAsync(seg, ctx->seg.p, (size_t)nPixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+
 int ssg_eliminate_small_segments(ssg_ctx *ctx, uint32_t *seg, const void *img, int dtype, int nBands,
                                  int64_t nRows, int64_t nCols, uint32_t maxSegId, int minSegSize,
                                  double spectralThreshold, int fourConnected, uint32_t minSegId,

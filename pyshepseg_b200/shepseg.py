@@ -308,6 +308,20 @@ def eliminateSinglePixels(img, seg, segSize, minSegId, maxSegId, fourConnected, 
         int(bool(fourConnected)), ctypes.byref(moved))
 
 
+def relabelSegments(seg, segSize, minSegId, context=None):
+    """
+    Recode seg in place so that segment ids are contiguous: ids from minSegId up that own no
+    pixel (segSize == 0) are squeezed out, the order of the others is kept (shepseg.py:739-777).
+    segSize is not updated, as in the reference.
+    """
+    ctx = context if context is not None else _lib.default_context()
+    _inplaceSeg(seg)
+    segSize = numpy.ascontiguousarray(segSize, dtype=numpy.uint32)
+    if seg.size and int(seg.max()) >= len(segSize):
+        raise ValueError('segSize has %d entries but seg holds id %d' % (len(segSize), int(seg.max())))
+    ctx.call('ssg_relabel_segments', _lib.ptr(seg), seg.size, _lib.ptr(segSize), len(segSize), int(minSegId))
+
+
 def eliminateSmallSegments(seg, img, maxSegId, minSegSize, maxSpectralDiff, fourConnected,
         minSegId, context=None):
     """
