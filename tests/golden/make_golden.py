@@ -7,7 +7,9 @@ in the development image).  Run from the repo root:
 
 The fixtures pin the CPU oracle (tests/test_oracle_golden.py) and, on a GPU box, the
 CUDA path (tests/test_gpu_parity.py).  /root/reference does not exist on the GPU box,
-so nothing at test time imports it; this script is the only place that does.
+so no GPU test, smoke() or bench.py imports it; besides this script only
+tests/test_oracle_vs_reference_live.py does (a CPU test that is skipped where the reference
+checkout does not exist).
 
 Every .npz holds the input image, the cluster centres given to both implementations,
 the call parameters and the reference's outputs after each stage of
