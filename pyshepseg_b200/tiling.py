@@ -240,12 +240,14 @@ def resolveTile(tables, rank, flags, pairKeys, pairCounts, offset, lutTop, lutLe
     the final-id tables of the upper / left neighbours, return (lut, trimmedMax).
     """
     n = int(tables.maxId) + 1
-    lut = numpy.zeros(n, dtype=numpy.uint32)
     if simpleTileRecode:
+        lut = numpy.zeros(n, dtype=numpy.uint32)
         lut[1:] = numpy.arange(1, n, dtype=numpy.uint64) + offset
     else:
-        numbered = (flags & _lib.SEG_NUMBERED) != 0
-        lut[numbered] = rank[numbered] + numpy.uint32(offset)
+        # (whole-array arithmetic instead of boolean fancy indexing: this runs on the critical
+        # path of the last tile, on a few hundred thousand segments)
+        isNumbered = ((flags & _lib.SEG_NUMBERED) != 0).astype(numpy.uint32)
+        lut = (rank.astype(numpy.uint32, copy=False) + numpy.uint32(offset)) * isNumbered
         if len(pairKeys) > 0:
             isLeft = (pairKeys >> numpy.uint64(63)) != 0
             segs = ((pairKeys >> numpy.uint64(32)) & numpy.uint64(0x7FFFFFFF)).astype(numpy.int64)
@@ -256,8 +258,8 @@ def resolveTile(tables, rank, flags, pairKeys, pairCounts, offset, lutTop, lutLe
                     continue
                 (k, mode) = _modeByKey(segs[sel], nbrLut[nbr[sel]].astype(numpy.int64), pairCounts[sel])
                 lut[k] = mode.astype(numpy.uint32)
-    inTrim = (flags & _lib.SEG_INTRIM) != 0
-    trimmedMax = int(lut[inTrim].max()) if inTrim.any() else 0
+    inTrim = ((flags & _lib.SEG_INTRIM) != 0).astype(numpy.uint32)
+    trimmedMax = int((lut * inTrim).max()) if n > 0 else 0
     return (lut, trimmedMax)
 
 
