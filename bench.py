@@ -23,9 +23,13 @@ the same shape (weak scaling; tiles of different scenes are independent, so the 
 no collective); NCCL broadcasts the cluster centres from rank 0 and all-gathers every scene's
 segment count per step, from which each scene's global id base follows.
 
---impl reference times the CPU restatement of the reference (oracle/, a plain C port of the
-numba / scikit-learn path, validated bit for bit against the reference) on the host cores, on a
-bounded sample of the same workload.
+--impl reference times the reference itself on the host cores: the UNMODIFIED pyshepseg 2.0.3
+(installed from /root/reference into the git-ignored baseline/_ref/, numba + scikit-learn) runs
+shepseg.doShepherdSegmentation in one process per core, each on its own crop of the workload
+raster, JIT warmed beforehand (cpu_baseline.kind "reference").  Where that install is missing it
+falls back to the C port of the path in oracle/ (kind "port"), which the GPU arm also times
+beside the numba figure.  Both are bounded samples of the same workload; pixels are credited as
+unique mosaic pixels (tile pixels divided by the workload's tile-pixel / unique-pixel ratio).
 """
 import argparse
 import json
@@ -123,8 +127,31 @@ def make_scene(wl, seed, out=None):
     return img
 
 
-def scene_centres(wl, img):
-    return synth.diagonal_centres(img, wl['numClusters'])
+def scene_centres(wl, img, seed=1):
+    """
+    Cluster centres of the workload: scikit-learn KMeans fitted the way the reference fits it
+    (fitSpectralClusters with fixedKMeansInit=True, shepseg.py:252-314) on a 1 % subsample of the
+    raster (every 10th row and column), cached on /tmp so that both arms use the same numbers.
+    """
+    cache = '/tmp/shepseg_bench_%s_seed%d_centres_k%d_%dx%d.npy' % (wl['name'], seed, wl['numClusters'],
+        img.shape[1], img.shape[2])
+    if os.path.exists(cache):
+        try:
+            c = numpy.load(cache)
+            if c.shape == (wl['numClusters'], img.shape[0]):
+                return c
+        except Exception:
+            pass
+    from pyshepseg_b200 import shepseg
+    sub = numpy.ascontiguousarray(img[:, ::10, ::10])
+    km = shepseg.fitSpectralClusters(sub, wl['numClusters'], 100, None, True)
+    c = numpy.ascontiguousarray(km.cluster_centers_, dtype=numpy.float64)
+    try:
+        numpy.save(cache + '.tmp.npy', c)
+        os.replace(cache + '.tmp.npy', cache)
+    except Exception:
+        pass
+    return c
 
 
 class ClockSampler(object):
@@ -187,25 +214,38 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------
-# the CPU arm: the oracle port of the reference on the host cores
+# the CPU arm: the unmodified reference (numba) on the host cores; the C port beside it
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(wl, img, centres, threads, tile=4096):
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def tile_pixel_ratio(tileInfo, nR, nC):
+    """tile pixels per unique pixel of the workload's tile layout (1.195 for 10980 / 4096 / 1024)"""
+    return sum(t[2] * t[3] for t in tileInfo.tiles.values()) / float(nR * nC)
+
+
+def crop_origins(wl, n, tile):
+    out = []
+    step = max(1, (wl['rows'] - tile) // max(1, n - 1)) if n > 1 else 0
+    for i in range(n):
+        y = min(i * step, wl['rows'] - tile)
+        x = min((i * 977) % max(1, wl['cols'] - tile), wl['cols'] - tile)
+        out.append((y, x))
+    return out
+
+
+def cpu_port_sample(wl, img, centres, threads, tile=4096):
     """
-    One bounded sample of the workload on the CPU: `threads` tiles of tile x tile pixels cut
-    from the raster, one per thread, each through the oracle's doShepherdSegmentation (the
-    reference's numba stages are single threaded; using all cores means one tile per core,
-    BASELINE.md section 3).  Returns (pixels, seconds).
+    One bounded sample of the workload through the C port of the path (oracle/): `threads` tiles
+    of tile x tile pixels cut from the raster, one per thread (the reference's numba stages are
+    single threaded; using all cores means one tile per core).
+    Returns (tile pixels, seconds).
     """
     os.environ['OMP_NUM_THREADS'] = '1'
     from oracle import oracle
     oracle.lib()
     km = KM(centres)
-    step = max(1, (wl['rows'] - tile) // max(1, threads - 1)) if threads > 1 else 0
-    crops = []
-    for i in range(threads):
-        y = min(i * step, wl['rows'] - tile)
-        x = min((i * 977) % max(1, wl['cols'] - tile), wl['cols'] - tile)
-        crops.append(numpy.ascontiguousarray(img[:, y:y + tile, x:x + tile]))
+    crops = [numpy.ascontiguousarray(img[:, y:y + tile, x:x + tile]) for (y, x) in crop_origins(wl, threads, tile)]
     done = [None] * threads
 
     def work(i):
@@ -221,35 +261,147 @@ def cpu_reference_sample(wl, img, centres, threads, tile=4096):
     return (threads * tile * tile, dt)
 
 
+def _numba_worker(conn, refDir, scenePath, origin, tile, wlDict, centres):
+    """One process of the numba arm: imports the unmodified reference from baseline/_ref, warms
+    the JIT on a 64 x 64 image, then segments its own crop every time it is told to."""
+    try:
+        os.environ['OMP_NUM_THREADS'] = '1'          # predict's OpenMP team: one core per process
+        os.environ['NUMBA_NUM_THREADS'] = '1'
+        sys.path.insert(0, refDir)
+        from pyshepseg import shepseg as ref
+        from sklearn.cluster import KMeans
+        import warnings
+        warnings.filterwarnings('ignore')
+        k = centres.shape[0]
+        km = KMeans(n_clusters=k, n_init=1, init=centres, max_iter=1)
+        km.fit(centres)                              # a fitted object whose predict() works ...
+        km.cluster_centers_ = numpy.ascontiguousarray(centres, dtype=numpy.float64)   # ... with OUR centres
+        scene = numpy.load(scenePath, mmap_mode='r')
+        (y, x) = origin
+        crop = numpy.ascontiguousarray(scene[:, y:y + tile, x:x + tile])
+        ref.doShepherdSegmentation(numpy.ascontiguousarray(crop[:, :64, :64]), minSegmentSize=wlDict['minSegmentSize'],
+            maxSpectralDiff=wlDict['maxSpectralDiff'], fourConnected=wlDict['fourConnected'], kmeansObj=km)
+        conn.send(('ready', ref.__file__))
+        while True:
+            msg = conn.recv()
+            if msg == 'stop':
+                break
+            size = int(msg)
+            sub = crop if size >= tile else numpy.ascontiguousarray(crop[:, :size, :size])
+            t0 = time.time()
+            res = ref.doShepherdSegmentation(sub, minSegmentSize=wlDict['minSegmentSize'],
+                maxSpectralDiff=wlDict['maxSpectralDiff'], fourConnected=wlDict['fourConnected'], kmeansObj=km)
+            conn.send(('done', time.time() - t0, int(res.segimg.max())))
+    except Exception as e:      # noqa
+        import traceback
+        conn.send(('error', traceback.format_exc()))
+
+
+class NumbaPool(object):
+    """`procs` processes, each holding the reference and one crop of the scene."""
+    def __init__(self, wl, scenePath, centres, procs, tile):
+        import multiprocessing
+        mp = multiprocessing.get_context('spawn')
+        self.procs = []
+        self.tile = tile
+        wlDict = dict((k, wl[k]) for k in ('minSegmentSize', 'maxSpectralDiff', 'fourConnected'))
+        for origin in crop_origins(wl, procs, tile):
+            (a, b) = mp.Pipe()
+            pr = mp.Process(target=_numba_worker, args=(b, REF_DIR, scenePath, origin, tile, wlDict, centres),
+                daemon=True)
+            pr.start()
+            self.procs.append((pr, a))
+        self.refFile = None
+        for (pr, a) in self.procs:
+            msg = a.recv()
+            if msg[0] != 'ready':
+                self.close()
+                raise RuntimeError('numba worker failed: %s' % (msg[1],))
+            self.refFile = msg[1]
+
+    def step(self, size=None):
+        """every process segments its crop (or its top-left size x size corner); (tile pixels, seconds)"""
+        size = self.tile if size is None else min(size, self.tile)
+        t0 = time.time()
+        for (pr, a) in self.procs:
+            a.send(size)
+        for (pr, a) in self.procs:
+            msg = a.recv()
+            if msg[0] != 'done':
+                self.close()
+                raise RuntimeError('numba worker failed: %s' % (msg[1],))
+        return (len(self.procs) * size * size, time.time() - t0)
+
+    def close(self):
+        for (pr, a) in self.procs:
+            try:
+                a.send('stop')
+            except Exception:
+                pass
+        for (pr, a) in self.procs:
+            pr.join(timeout=5)
+            if pr.is_alive():
+                pr.kill()
+        self.procs = []
+
+
+def scene_path(wl, seed=1):
+    return '/tmp/shepseg_bench_%s_seed%d.npy' % (wl['name'], seed)
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    threads = min(cores, 64)      # one tile per host thread (the reference's numba stages are single threaded)
-    tile = 2048 if args.quick else 4096
+    procs = min(cores, 64)      # one tile per host core (the reference's numba stages are single threaded)
     img = make_scene(wl, seed=1)
     centres = scene_centres(wl, img)
     from pyshepseg_b200 import tiling
     (gr, gc) = SCENE_GRID.get(args.gpus, (1, args.gpus))
     tileInfo = tiling.getTilesForFile((wl['cols'] * gc, wl['rows'] * gr), wl['tileSize'], wl['overlapSize'])
-    for _ in range(args.warmup):
-        cpu_reference_sample(wl, img, centres, threads, tile=min(tile, 1024))
+    ratio = tile_pixel_ratio(tileInfo, wl['rows'] * gr, wl['cols'] * gc)
+    haveRef = os.path.isdir(os.path.join(REF_DIR, 'pyshepseg')) and os.path.exists(scene_path(wl)) \
+        and not args.port_only
     pix = 0
     secs = 0.0
-    for _ in range(args.steps):
-        (p, s) = cpu_reference_sample(wl, img, centres, threads, tile=tile)
-        pix += p
-        secs += s
-    value = pix / secs / 1e6
-    sample = '%d tiles of %dx%dx%d cut from the workload raster per step, one per thread' % (
-        threads, tile, tile, wl['bands'])
+    if haveRef:
+        # a step = one crop per core through the unmodified reference; crops of 2048 pixels keep a
+        # driver-length run (25 steps) within a few minutes at ~3 Mpixel/s per core
+        tile = 1024 if args.quick else 2048
+        pool = NumbaPool(wl, scene_path(wl), centres, procs, tile)
+        try:
+            for _ in range(args.warmup):
+                pool.step(256)
+            for _ in range(args.steps):
+                (p, s) = pool.step()
+                pix += p
+                secs += s
+        finally:
+            pool.close()
+        kind = 'reference'
+        sample = ('%d crops of %dx%dx%d of the workload raster per step, one per process, through the unmodified '
+            'pyshepseg %s doShepherdSegmentation (numba JIT warmed; no stitch); pixels credited as unique mosaic '
+            'pixels = tile pixels / %.3f' % (procs, tile, tile, wl['bands'], '2.0.3', ratio))
+    else:
+        tile = 2048 if args.quick else 4096
+        for _ in range(args.warmup):
+            cpu_port_sample(wl, img, centres, procs, tile=min(tile, 1024))
+        for _ in range(args.steps):
+            (p, s) = cpu_port_sample(wl, img, centres, procs, tile=tile)
+            pix += p
+            secs += s
+        kind = 'port'
+        sample = ('%d tiles of %dx%dx%d cut from the workload raster per step, one per thread, through the C port '
+            'of the path (oracle/; baseline/_ref not installed); pixels credited as unique mosaic pixels = tile '
+            'pixels / %.3f' % (procs, tile, tile, wl['bands'], ratio))
+    value = pix / ratio / secs / 1e6
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16',
         'data': 'synthetic', 'config': workload_config(wl, args.gpus, None, tileInfo),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -346,21 +498,17 @@ def run_ours(args, wl):
         return (seg, maxSegId)
 
     def step_e2e():
+        # the call a user makes: doTiledShepherdSegmentation, raster in (pinned) host memory, the
+        # mosaic delivered into host memory, copies inside
         cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=E2E_WORKERS,
             devices=[local], tileCompletionTimeout=600)
-        sink = rasterfile.MemorySink.__new__(rasterfile.MemorySink)
-        sink.array = pinnedOut.array
-        sink.yoff = y0
-        sink.metadata = {}
-        sink.nodata = None
-        sink.hist = None
-        src = rasterfile.MemoryRaster(img)
-        src.yoff = y0
-        seg = tiling.TiledSegmenter(src, range(1, nB + 1), tileInfo,
-            wl['overlapSize'], centres, None, wl['fourConnected'], wl['minSegmentSize'], thr, False, cfg,
-            timinghooks.Timers())
-        (maxSegId, hist) = seg.run(sink, comm)
-        return (seg, maxSegId)
+        cfg.comm = comm
+        sink = rasterfile.MemorySink(nC, bandRows, array=pinnedOut.array, yoff=y0)
+        src = rasterfile.MemoryRaster(img, yoff=y0, fullYsize=nR)
+        res = tiling.doTiledShepherdSegmentation(src, sink, tileSize=wl['tileSize'], overlapSize=wl['overlapSize'],
+            minSegmentSize=wl['minSegmentSize'], numClusters=wl['numClusters'], maxSpectralDiff=wl['maxSpectralDiff'],
+            fourConnected=wl['fourConnected'], kmeansObj=km, concurrencyCfg=cfg, returnGDALDS=True)
+        return (res, int(res.maxSegId))
 
     def exchange_ids(maxSegId):
         return 0      # (ids are global already: the sharded stitch numbers the mosaic as a whole)
@@ -427,7 +575,7 @@ def run_ours(args, wl):
     # other streams' kernels)
     (msProfiled, lastProf) = timed(resident_profiled, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    if os.environ.get('SSG_TIMELINE') and rank == 0:
+    if os.environ.get('SSG_TIMELINE') and rank == 0 and lastE2E[0].timeline:
         for (ms, what) in sorted(lastE2E[0].timeline):
             print('  %8.2f  %s' % (ms, what), file=sys.stderr)
 
@@ -498,14 +646,62 @@ def run_ours(args, wl):
                 gbs = b * tilePixels * args.steps / (kernelAgg[name][1] / 1e3) / 1e9
                 extra[name] = {'achieved': gbs, 'frac': gbs / peak, 'bytes_per_pixel': b}
 
+        # ---- the CPU path beside it (rank 0, N = 1 only): the unmodified reference (numba) in a
+        # child process of this script, and the C port in threads here
         cpu = None
+        cpuPort = None
+        ratio = tile_pixel_ratio(tileInfo, nR, nC)
         if args.gpus == 1 and not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 64)
             tile = 2048 if args.quick else 4096
-            (p, s) = cpu_reference_sample(wl, img, centres, threads, tile=tile)
-            cpu = {'value': p / s / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                'sample': '%d tiles of %dx%dx%d cut from the workload raster, one per thread (%.1f s)' % (
-                    threads, tile, tile, nB, s)}
+            (p, s) = cpu_port_sample(wl, img, centres, threads, tile=tile)
+            cpuPort = {'value': p / ratio / s / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                'sample': '%d tiles of %dx%dx%d cut from the workload raster, one per thread (%.1f s); unique-pixel '
+                    'credit = tile pixels / %.3f' % (threads, tile, tile, nB, s, ratio)}
+            cpu = cpuPort
+            try:
+                cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '1']
+                if args.quick:
+                    cmd.append('--quick')
+                out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, check=True)
+                ref = json.loads(out.stdout.decode().strip().splitlines()[-1])['cpu_baseline']
+                if ref.get('kind') == 'reference':
+                    cpu = ref
+            except Exception as e:
+                print('numba reference sample failed: %r' % (e,), file=sys.stderr)
+
+        # ---- parity of the BENCHED mosaic: the host-to-host result of the last timed step against
+        # the CPU oracle run on the same raster (every tile through oracle.doShepherdSegmentation on
+        # the host threads, then oracle.stitchTiles), outside the timed regions
+        parity = None
+        mosaicCrc = None
+        if args.gpus == 1 and not args.no_parity:
+            import zlib
+            from oracle import oracle
+            oracle.lib()
+            t0 = time.time()
+            kmO = KM(centres)
+            keys = sorted(tileInfo.tiles.keys(), key=lambda cr: -tileInfo.tiles[cr][2] * tileInfo.tiles[cr][3])
+            segs = {}
+
+            def oracleTile(cr):
+                (x, y, xs, ys) = tileInfo.tiles[cr]
+                sub = numpy.ascontiguousarray(img[:, y:y + ys, x:x + xs])
+                segs[cr] = oracle.doShepherdSegmentation(sub, minSegmentSize=wl['minSegmentSize'],
+                    maxSpectralDiff=wl['maxSpectralDiff'], fourConnected=wl['fourConnected'], kmeansObj=kmO).segimg
+            ths = [threading.Thread(target=oracleTile, args=(cr,)) for cr in keys]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            oti = oracle.getTilesForFile(nC, nR, wl['tileSize'], wl['overlapSize'])
+            (mosaicO, maxO, histO) = oracle.stitchTiles(segs, oti, nC, nR, wl['overlapSize'])
+            same = bool(numpy.array_equal(mosaicO, pinnedOut.array)) and int(maxO) == int(lastE2E[1])
+            mosaicCrc = '%08x' % (zlib.crc32(pinnedOut.array) & 0xffffffff)
+            parity = {'equal': same, 'segments': int(maxO), 'oracle_crc32': '%08x' % (zlib.crc32(mosaicO) & 0xffffffff),
+                'seconds': round(time.time() - t0, 1),
+                'what': 'e2e mosaic of the last timed step vs oracle (per-tile C port + stitch) on the same raster'}
+            del mosaicO, segs
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': msResident / args.steps, 'higher_is_better': True,
@@ -516,7 +712,9 @@ def run_ours(args, wl):
                 'workers': E2E_WORKERS, 'same_labels_as_resident': sameMosaic},
             'gpu_launches': int(launchesResident),
             'roofline': roof, 'roofline_other': extra, 'kernels': kernels,
-            'cpu_baseline': cpu, 'clocks': clocks,
+            'cpu_baseline': cpu, 'cpu_baseline_port': cpuPort, 'clocks': clocks,
+            'parity_vs_oracle': None if parity is None else parity['equal'], 'parity': parity,
+            'mosaic_crc32': mosaicCrc,
             'segments_per_scene': int(lastRes[1]),
             'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastProf[0].stageMs.items()),
             'per_rank': perRank,
@@ -546,6 +744,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--quick', action='store_true', help='2048-pixel raster and tiles (smoke runs only)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle check of the benched mosaic')
+    ap.add_argument('--port-only', action='store_true', help='reference arm: time the C port even if baseline/_ref exists')
     ap.add_argument('--verbose-steps', action='store_true', help='print every timed step (stderr)')
     args = ap.parse_args()
     wl = dict(WORKLOAD)

@@ -237,15 +237,40 @@ class Context(object):
         self.call('ssg_memcpy_d2h', ptr(dst), src, dst.nbytes if nbytes is None else nbytes)
 
 
-_defaultCtx = {}
+# Default contexts: one per (thread, device), held in thread-local storage so that a context
+# (its stream, pinned words and multi-gigabyte scratch slab) dies with the thread that made it
+# instead of piling up under reused thread idents.  Callers that run their own threads for long
+# should pass context= explicitly and close it themselves.
+_defaultLocal = threading.local()
+_defaultAll = set()
 _defaultLock = threading.Lock()
+
+
+class _ThreadContexts(object):
+    """The contexts of one thread; closing them when the thread-local storage is collected."""
+    def __init__(self):
+        self.byDevice = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        for ctx in self.byDevice.values():
+            with _defaultLock:
+                _defaultAll.discard(ctx)
+            ctx.close()
+        self.byDevice = {}
 
 
 def _closeDefaultContexts():
     with _defaultLock:
-        for ctx in _defaultCtx.values():
-            ctx.close()
-        _defaultCtx.clear()
+        ctxs = list(_defaultAll)
+        _defaultAll.clear()
+    for ctx in ctxs:
+        ctx.close()
 
 
 atexit.register(_closeDefaultContexts)
@@ -253,10 +278,13 @@ atexit.register(_closeDefaultContexts)
 
 def default_context(device=0):
     """A per-thread, per-device context for the simple (single call) entry points."""
-    key = (threading.get_ident(), int(device))
-    with _defaultLock:
-        ctx = _defaultCtx.get(key)
-        if ctx is None or ctx.h is None:
-            ctx = Context(device)
-            _defaultCtx[key] = ctx
-        return ctx
+    holder = getattr(_defaultLocal, 'holder', None)
+    if holder is None:
+        holder = _defaultLocal.holder = _ThreadContexts()
+    ctx = holder.byDevice.get(int(device))
+    if ctx is None or ctx.h is None:
+        ctx = Context(device)
+        holder.byDevice[int(device)] = ctx
+        with _defaultLock:
+            _defaultAll.add(ctx)
+    return ctx

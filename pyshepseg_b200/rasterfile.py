@@ -51,7 +51,10 @@ class RasterSource(object):
 
 
 class MemoryRaster(RasterSource):
-    def __init__(self, img, nodata=None):
+    """A (count, ysize, xsize) array as a raster.  With `yoff` / `fullYsize` the array is the row
+    band [yoff, yoff + ysize) of a taller raster of fullYsize rows: what one rank of a sharded
+    run holds of the mosaic (window reads are then relative to the band)."""
+    def __init__(self, img, nodata=None, yoff=0, fullYsize=None):
         img = numpy.asarray(img)
         if img.ndim == 2:
             img = img[None]
@@ -59,6 +62,8 @@ class MemoryRaster(RasterSource):
         (self.count, self.ysize, self.xsize) = img.shape
         self.dtype = img.dtype
         self.nodata = [nodata] * self.count
+        self.yoff = int(yoff)
+        self.fullYsize = self.ysize if fullYsize is None else int(fullYsize)
 
     def readWindow(self, bandNumbers, xoff, yoff, xsize, ysize, out=None):
         if out is None:
@@ -273,11 +278,35 @@ class RasterSink(object):
 
 
 class MemorySink(RasterSink):
-    def __init__(self, xsize, ysize, dtype=numpy.uint32):
-        self.array = numpy.zeros((ysize, xsize), dtype=dtype)
+    """The output raster as a numpy array.  `array` (optional) is caller-owned memory to write
+    into, e.g. pinned host memory; with `yoff` it is the row band of a taller mosaic that starts
+    at mosaic row yoff (one rank of a sharded run).  Overviews are kept per level in
+    `overviews` when `levels` is given (tiling.py:1360-1383)."""
+    levels = ()
+    overviews = {}
+    yoff = 0
+
+    def __init__(self, xsize, ysize, dtype=numpy.uint32, array=None, yoff=0, levels=None):
+        if array is None:
+            array = numpy.zeros((ysize, xsize), dtype=dtype)
+        elif array.shape != (ysize, xsize):
+            raise RasterError('array of shape %s given for a %d x %d raster' % (array.shape, ysize, xsize))
+        self.array = array
+        self.yoff = int(yoff)
         self.metadata = {}
         self.nodata = None
         self.hist = None
+        self.levels = list(levels) if levels else []
+        self.overviews = dict((lvl, numpy.zeros((-(-ysize // lvl), -(-xsize // lvl)), dtype=dtype))
+            for lvl in self.levels)
+
+    def writeOverviews(self, arr, xoff, yoff):
+        for lvl in self.levels:
+            ov = self.overviews[lvl]
+            sub = arr[lvl // 2::lvl, lvl // 2::lvl]
+            (xs, ys) = (xoff // lvl, yoff // lvl)
+            sub = sub[:ov.shape[0] - ys, :ov.shape[1] - xs]
+            ov[ys:ys + sub.shape[0], xs:xs + sub.shape[1]] = sub
 
     def write(self, arr, xoff, yoff):
         self.array[yoff:yoff + arr.shape[0], xoff:xoff + arr.shape[1]] = arr
@@ -382,6 +411,24 @@ class TiffSink(MemorySink):
             _sidecar(self.filename, self.nodata, self.metadata, self.hist)
 
 
+def overviewLevels(xsize, ysize, finalOutSize=1024):
+    """
+    The overview levels the reference sets up (setupOverviews, tiling.py:1385-1404): 4, 8, ...
+    The reference appends a level and only then re-tests the SAME level before moving on, so it
+    always emits one level more than "while the overview is at least 1024 pixels" would
+    (10980 pixels -> [4, 8, 16]); that is kept.
+    """
+    outSize = max(int(xsize), int(ysize))
+    levels = []
+    i = 2
+    ok = (outSize // (2 ** i)) >= finalOutSize
+    while ok:
+        levels.append(2 ** i)
+        ok = (outSize // (2 ** i)) >= finalOutSize
+        i += 1
+    return levels
+
+
 class GdalSink(RasterSink):      # pragma: no cover - exercised only where GDAL exists
     """Output through GDAL exactly as the reference sets it up (tiling.py:961-975, 1343-1404)."""
     def __init__(self, filename, xsize, ysize, driver, options, source):
@@ -392,15 +439,7 @@ class GdalSink(RasterSink):      # pragma: no cover - exercised only where GDAL 
         if source is not None:
             self.ds.SetProjection(source.projection)
             self.ds.SetGeoTransform(source.geotransform)
-        outSize = max(xsize, ysize)
-        self.levels = []
-        i = 2
-        while (outSize // (2 ** i)) >= 1024:
-            self.levels.append(2 ** i)
-            i += 1
-        if (outSize // 4) >= 1024 or self.levels:
-            if not self.levels:
-                self.levels = [4]
+        self.levels = overviewLevels(xsize, ysize)
         self.ds.BuildOverviews("NEAREST", self.levels)
         self.band = self.ds.GetRasterBand(1)
         self.band.SetMetadataItem('LAYER_TYPE', 'thematic')

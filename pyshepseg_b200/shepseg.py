@@ -302,6 +302,9 @@ def eliminateSinglePixels(img, seg, segSize, minSegId, maxSegId, fourConnected, 
     _inplaceSeg(seg)
     if not (segSize.dtype == numpy.uint32 and segSize.flags.c_contiguous):
         raise ValueError('segSize must be a C-contiguous uint32 array')
+    # the kernels index segSize by segment id without a bound check of their own
+    if seg.size and int(seg.max()) >= len(segSize):
+        raise ValueError('segSize has %d entries but seg holds id %d' % (len(segSize), int(seg.max())))
     moved = ctypes.c_int64(0)
     ctx.call('ssg_eliminate_single_pixels', _lib.ptr(dimg), _lib.DTYPE_CODES[dimg.dtype], nBands,
         nRows, nCols, _lib.ptr(seg), _lib.ptr(segSize), len(segSize), int(minSegId),
@@ -333,6 +336,9 @@ def eliminateSmallSegments(seg, img, maxSegId, minSegSize, maxSpectralDiff, four
     dimg = _deviceImage(img)
     (nBands, nRows, nCols) = dimg.shape
     _inplaceSeg(seg)
+    # the per-segment tables have maxSegId + 1 entries and are indexed by segment id
+    if seg.size and int(seg.max()) > int(maxSegId):
+        raise ValueError('seg holds id %d, above maxSegId=%d' % (int(seg.max()), int(maxSegId)))
     numElim = ctypes.c_int64(0)
     ctx.call('ssg_eliminate_small_segments', _lib.ptr(seg), _lib.ptr(dimg),
         _lib.DTYPE_CODES[dimg.dtype], nBands, nRows, nCols, int(maxSegId), int(minSegSize),

@@ -514,12 +514,18 @@ class TiledSegmenter(object):
             t.uses = int(t.col + 1 < tileInfo.ncols) + int(t.row + 1 < tileInfo.nrows)
             if (t.ysize < self.overlapSize or t.xsize < self.overlapSize) and len(self.tiles) > 1:
                 raise PyShepSegTilingError("tiles must be at least overlapSize pixels on a side")
+        if numpy.dtype(src.dtype).newbyteorder('=') not in _lib.DTYPE_CODES:
+            raise PyShepSegTilingError("rasters of type {} are not supported (supported: {})".format(
+                src.dtype, ', '.join(str(d) for d in _lib.DTYPE_CODES)))
+        if len(self.bandNumbers) > _lib.SSG_MAX_BANDS:
+            raise PyShepSegTilingError("at most {} bands are supported".format(_lib.SSG_MAX_BANDS))
         if len(set(self.cfg.devices)) > 1:
             raise PyShepSegTilingError('one process drives one GPU; use one process per GPU '
                 '(torchrun) for more, as bench.py --gpus N does')
         self.device = self.cfg.devices[0]
         self.readSemaphore = threading.BoundedSemaphore(max(1, self.cfg.maxConcurrentReads))
         self.forceExit = threading.Event()
+        self.workerError = None
         self.stageMs = {'assign': 0.0, 'clump': 0.0, 'single': 0.0, 'small': 0.0, 'total': 0.0}
         self.launches = 0
         self.h2dBytes = 0
@@ -641,26 +647,38 @@ class TiledSegmenter(object):
             slot.ctx.call('ssg_ctx_reserve', 0, 0, 0, maxStrip * 24 + (64 << 20))
 
     def _worker(self, slot, pool, inQue):
-        """A segmentation worker (tiling.py:1560-1613): pops tiles until the queue is empty."""
-        with slot.lock:
-            self._reserve(slot, True)
-            before = slot.ctx.launch_count()
-            self._profileStart(slot)
-            while not self.forceExit.is_set():
-                try:
-                    cr = inQue.get(block=False)
-                except queue.Empty:
-                    break
-                tile = self.tiles[cr]
-                try:
+        """A segmentation worker (tiling.py:1560-1613): pops tiles until the queue is empty.  Whatever
+        goes wrong -- reserving memory included -- is recorded where the stitch loop looks
+        (tile.error, like the reference's WorkerErrorRecord / checkWorkerExceptions) and every
+        tile still waiting is released, so the main thread fails at once with the real cause."""
+        tile = None
+        try:
+            with slot.lock:
+                self._reserve(slot, True)
+                before = slot.ctx.launch_count()
+                self._profileStart(slot)
+                while not self.forceExit.is_set():
+                    try:
+                        cr = inQue.get(block=False)
+                    except queue.Empty:
+                        break
+                    tile = self.tiles[cr]
                     self.segmentOne(slot, pool, tile)
-                except Exception as e:     # reported by the stitch loop, like WorkerErrorRecord
-                    tile.error = e
-                    self.forceExit.set()
-                tile.done.set()
-            self._profileStop(slot)
-            with self.statLock:
-                self.launches += slot.ctx.launch_count() - before
+                    tile.done.set()
+                    tile = None
+                self._profileStop(slot)
+                with self.statLock:
+                    self.launches += slot.ctx.launch_count() - before
+        except Exception as e:
+            self.workerError = e
+            self.forceExit.set()
+            if tile is not None:
+                tile.error = e
+            for t in self.tiles.values():      # nobody will segment these now
+                if not t.done.is_set():
+                    if t.error is None:
+                        t.error = e
+                    t.done.set()
 
     def _profileStart(self, slot):
         if self.profile:
@@ -1157,19 +1175,27 @@ def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
             raise PyShepSegTilingError(str(e))
         if bandNumbers is None:
             bandNumbers = range(1, src.count + 1)
+        # one process per GPU (torchrun): concurrencyCfg.comm is a distributed.TorchComm, `src` is
+        # this rank's row band of the raster and `outfile` the sink of this rank's windows
+        comm = getattr(concurrencyCfg, 'comm', None)
+        sharded = comm is not None and comm.world > 1
+        fullYsize = getattr(src, 'fullYsize', src.ysize)
         if kmeansObj is None:
+            if sharded:
+                raise PyShepSegTilingError("a sharded run needs kmeansObj (fit on one rank, "
+                    "broadcast the centres)")
             with timings.interval('spectralclusters'):
                 (kmeansObj, subsamplePcnt, imgNullVal) = fitSpectralClustersWholeFile(src,
                     bandNumbers, numClusters, subsamplePcnt, imgNullVal, fixedKMeansInit)
         elif imgNullVal is None:
             imgNullVal = getImgNullValue(src, bandNumbers)
-        tileInfo = getTilesForFile(src, tileSize, overlapSize)
+        tileInfo = getTilesForFile((src.xsize, fullYsize), tileSize, overlapSize)
         if verbose:
             print("Found {} tiles, with {} rows and {} cols".format(tileInfo.getNumTiles(),
                 tileInfo.nrows, tileInfo.ncols))
         msd = shepseg.autoMaxSpectralDiff(kmeansObj, maxSpectralDiff, spectDistPcntile)
         try:
-            sink = rasterfile.createRaster(outfile, src.xsize, src.ysize, outputDriver,
+            sink = rasterfile.createRaster(outfile, src.xsize, fullYsize, outputDriver,
                 creationOptions, source=src)
         except rasterfile.RasterError as e:
             raise PyShepSegTilingError(str(e))
@@ -1178,10 +1204,12 @@ def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
         seg = TiledSegmenter(src, bandNumbers, tileInfo, overlapSize, shepseg._centres(kmeansObj),
             imgNullVal, fourConnected, minSegmentSize, shepseg.spectralThreshold(msd),
             simpleTileRecode, concurrencyCfg, timings, verbose)
-        (maxSegId, hist) = seg.run(sink)
-        sink.writeHistogram(hist)
-        result.hasEmptySegments = checkForEmptySegments(hist, overlapSize)
-        estimateStatsFromHisto(sink, hist)
+        (maxSegId, hist) = seg.run(sink, comm)
+        if len(hist) > 0:          # (ranks other than 0 of a sharded run hold no histogram)
+            if writeHistogram:
+                sink.writeHistogram(hist)
+            result.hasEmptySegments = checkForEmptySegments(hist, overlapSize)
+            estimateStatsFromHisto(sink, hist)
         if returnGDALDS:
             result.outDs = getattr(sink, 'ds', sink)
         else:
@@ -1200,4 +1228,5 @@ def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
     result.gpuLaunches = seg.launches
     result.h2dBytes = seg.h2dBytes
     result.d2hBytes = seg.d2hBytes
+    result.timeline = seg.timeline
     return result

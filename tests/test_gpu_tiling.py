@@ -139,3 +139,32 @@ def test_whole_file_kmeans_fit(tiling):
     (mosaic, maxSegId, hist) = oracle_tiled(img, res.kmeans, 512, 64, 30, None, True)
     same(res.outDs.array, mosaic, 'mosaic with fitted centres')
     assert res.timings.getDurationsForName('spectralclusters') is not None
+
+
+def test_worker_failure_surfaces_at_once(tiling):
+    """A worker that dies (here: the raster read raises) must make the call fail quickly with the
+    real cause, not with a tile-completion timeout (tiling.py:926-928, checkWorkerExceptions)"""
+    import time
+
+    class Broken(rasterfile.MemoryRaster):
+        def readWindow(self, *a, **k):
+            raise IOError('disk on fire')
+    img = synth.synth_v1(600, 600, 3, seed=3)
+    src = Broken(img)
+    src.img = None        # not addressable in place: every tile goes through readWindow
+    km = goldenutil.Centres(synth.diagonal_centres(img, 10))
+    cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=2,
+        tileCompletionTimeout=30)
+    t0 = time.time()
+    with pytest.raises(tiling.PyShepSegTilingError, match='disk on fire'):
+        tiling.doTiledShepherdSegmentation(src, None, tileSize=256, overlapSize=64, minSegmentSize=20,
+            kmeansObj=km, outputDriver='MEM', concurrencyCfg=cfg)
+    assert time.time() - t0 < 20
+
+
+def test_unsupported_raster_type_is_a_tiling_error(tiling):
+    img = numpy.zeros((2, 64, 64), dtype=numpy.float32)
+    km = goldenutil.Centres(numpy.zeros((3, 2)))
+    with pytest.raises(tiling.PyShepSegTilingError, match='not supported'):
+        tiling.doTiledShepherdSegmentation(rasterfile.MemoryRaster(img), None, tileSize=32, overlapSize=8,
+            kmeansObj=km, outputDriver='MEM')

@@ -101,3 +101,35 @@ def test_argument_errors():
     with pytest.raises(ValueError):
         tiling.doTiledShepherdSegmentation(img, None, outputDriver='MEM',
             concurrencyCfg=tiling.SegmentationConcurrencyConfig(concurrencyType='bogus'))
+
+
+def test_overview_levels_follow_the_reference_loop():
+    """setupOverviews (tiling.py:1385-1404) appends a level, re-tests the same level and only then
+    moves on: one level more than a plain `while size // level >= 1024` gives."""
+    assert rasterfile.overviewLevels(10980, 10980) == [4, 8, 16]
+    assert rasterfile.overviewLevels(4096, 100) == [4, 8]
+    assert rasterfile.overviewLevels(4000, 3000) == []
+    assert rasterfile.overviewLevels(40000, 40000) == [4, 8, 16, 32, 64]
+
+
+def test_memory_sink_overviews_and_caller_array():
+    """writeOverviews takes arr[L//2::L, L//2::L] at (xoff//L, yoff//L) (tiling.py:1360-1383)"""
+    full = numpy.arange(40 * 64, dtype=numpy.uint32).reshape(40, 64)
+    mine = numpy.zeros((40, 64), dtype=numpy.uint32)
+    sink = rasterfile.MemorySink(64, 40, array=mine, levels=[4, 8])
+    for (y, x) in ((0, 0), (0, 32), (24, 0), (24, 32)):
+        win = full[y:y + 24, x:x + 32]
+        sink.write(win, x, y)
+        sink.writeOverviews(win, x, y)
+    assert sink.array is mine and numpy.array_equal(mine, full)
+    assert numpy.array_equal(sink.overviews[4], full[2::4, 2::4])
+    assert numpy.array_equal(sink.overviews[8], full[4::8, 4::8])
+    with pytest.raises(rasterfile.RasterError):
+        rasterfile.MemorySink(10, 10, array=mine)
+
+
+def test_memory_raster_row_band_view():
+    img = numpy.arange(2 * 6 * 5, dtype=numpy.uint16).reshape(2, 6, 5)
+    band = rasterfile.MemoryRaster(img[:, 2:5], yoff=2, fullYsize=6)
+    assert (band.ysize, band.fullYsize, band.yoff) == (3, 6, 2)
+    assert rasterfile.MemoryRaster(img).fullYsize == 6
