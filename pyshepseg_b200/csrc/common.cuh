@@ -46,6 +46,7 @@ struct ssg_ctx {
     DevBuf emuStack;
     DevBuf centres;   // double k*nBands
     std::vector<double> centresStage;
+    std::vector<unsigned long long> grownStartStage;   // host copy of the merge kernel's list offsets
     DevBuf counters;  // small device counter block (see enum Counter)
     DevBuf stitch0, stitch1, stitch2, stitch3, stitch4, stitch5;
 

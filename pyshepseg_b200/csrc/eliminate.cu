@@ -24,6 +24,7 @@
 // The whole targetSize loop runs as one persistent cooperative kernel (grid.sync between
 // phases) so that ~100 passes do not cost ~500 launches and host round trips.
 #include "common.cuh"
+#include "merge.cuh"
 
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -535,11 +536,6 @@ enum SmallCtr {
     SC_ELIM,          // merges done
     SC_PASSES,
     SC_COUNT = 16
-};
-
-struct SmallBarrier {
-    unsigned arrive;
-    unsigned pad[31];
 };
 
 struct SmallState {
@@ -1177,6 +1173,50 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     SSG_PROF_BEGIN(ctx, "k_list_sort");
     k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(sliceOff, sliceLen, len, pix);
     SSG_LAUNCHED(ctx);
+
+    if (regions && !getenv("SSG_SMALL_LEGACY")) {
+        // region mode: the passes of merge.cu (32-byte segment records, per-size candidate lists,
+        // grid kernel for the first sizes + one cluster for the tail)
+        const size_t m1g = (size_t)minSegSize + 1;
+        ctx->grownStartStage.assign(m1g, 0ull);
+        unsigned long long total = 0;
+        for (size_t z = 0; z < m1g; z++) {
+            ctx->grownStartStage[z] = total;
+            // a merge at size t makes at least 2t+1 >= 3 pixels; the segments that ever have exactly
+            // z pixels are disjoint sets of listed pixels
+            if (z >= 3) total += numSmallPix / z;
+        }
+        SSG_TRY(ssg_reserve(ctx, ctx->lut, ssgk_merge_rec_bytes(nB, len)));
+        SSG_TRY(ssg_reserve(ctx, ctx->targetList, (size_t)(total + 1) * sizeof(unsigned)));
+        SSG_TRY(ssg_reserve(ctx, ctx->sortKeys0, m1g * sizeof(unsigned long long) + m1g * sizeof(unsigned) +
+                                                 2 * (size_t)len * sizeof(unsigned) + 256 * sizeof(unsigned long long) +
+                                                 ssgk_merge_ctr_bytes() + 64));
+        unsigned long long *grownStart = bufp<unsigned long long>(ctx->sortKeys0);
+        unsigned long long *pendHead64 = grownStart + m1g;
+        unsigned long long *dbg = pendHead64 + len;
+        unsigned long long *mctr = dbg + 256;
+        unsigned *grownCount = reinterpret_cast<unsigned *>(
+            reinterpret_cast<char *>(mctr) + ssgk_merge_ctr_bytes());
+        SSG_CUDA(ctx, cudaMemcpyAsync(grownStart, ctx->grownStartStage.data(), m1g * sizeof(unsigned long long),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        SSG_CUDA(ctx, cudaMemsetAsync(pendHead64, 0, (size_t)len * sizeof(unsigned long long), ctx->stream));
+        SSG_CUDA(ctx, cudaMemsetAsync(grownCount, 0, m1g * sizeof(unsigned), ctx->stream));
+        MergeState ms;
+        ms.seg = seg; ms.segSize = segSize; ms.rec = bufp<unsigned>(ctx->lut); ms.pix = pix;
+        ms.mergeTo = bufp<unsigned>(ctx->mergeTo); ms.pendHead = pendHead64; ms.pendNext = bufp<unsigned>(ctx->pendNext);
+        ms.bucketStart = bucketStart; ms.bucketList = bucketList;
+        ms.grownList = bufp<unsigned>(ctx->targetList); ms.grownStart = grownStart; ms.grownCount = grownCount;
+        ms.ctr = mctr;
+        ms.bar = reinterpret_cast<SmallBarrier *>(mctr + 16);
+        ms.dbg = getenv("SSG_SMALL_DEBUG") ? dbg : nullptr;
+        if (ms.dbg) SSG_CUDA(ctx, cudaMemsetAsync(dbg, 0, 256 * sizeof(unsigned long long), ctx->stream));
+        ms.switchCands = 0; ms.switchMinT = 2;
+        ms.nB = nB; ms.nRows = (unsigned)nRows; ms.nCols = (unsigned)nCols; ms.four = four;
+        ms.minSegSize = minSegSize; ms.thr = thr;
+        MergePlan plan;
+        plan.fsum = bufp<float>(ctx->fsum); plan.sliceOff = sliceOff; plan.len = len;
+        return ssgk_merge_regions(ctx, ms, plan, numPasses, numElim);
+    }
 
     SmallState st;
     st.seg = seg; st.segSize = segSize; st.fsum = bufp<float>(ctx->fsum);

@@ -1,0 +1,48 @@
+// merge.cuh -- interface between eliminate.cu (which prepares spectra, buckets and pixel lists) and
+// merge.cu (the passes themselves, region mode).
+#pragma once
+#include "common.cuh"
+
+struct SmallBarrier {
+    unsigned arrive;
+    unsigned pad[31];
+};
+
+// words of one segment record {float sums[NBMAX]; uint size; uint listOffset; pad}: 32 / 64 / 128 bytes
+template <int NBMAX>
+struct MergeRecWords { static constexpr int value = NBMAX <= 4 ? 8 : (NBMAX <= 8 ? 16 : 32); };
+
+struct MergeState {
+    unsigned *seg;
+    unsigned *segSize;                 // kept in step for the relabel that follows (0 = dead)
+    unsigned *rec;                     // len records
+    unsigned *pix;                     // per-segment list regions of regionCap entries
+    unsigned *mergeTo;                 // len, zeroed
+    unsigned long long *pendHead;      // len, zeroed: (pass stamp << 32) | last pushed source
+    unsigned *pendNext;                // len
+    const unsigned *bucketStart;       // minSegSize + 1
+    const unsigned *bucketList;        // initially small segments grouped by size
+    unsigned *grownList;               // per size: targets that grew to exactly that size
+    const unsigned long long *grownStart;   // minSegSize + 1 offsets into grownList
+    unsigned *grownCount;              // minSegSize + 1, zeroed
+    unsigned long long *ctr;           // counters (2 x MC_COUNT), then the SmallBarrier
+    SmallBarrier *bar;
+    unsigned long long *dbg;
+    unsigned safe;                     // debugging switches (SSG_MERGE_SAFE)
+    unsigned switchCands, switchMinT;  // hand over to the cluster kernel at the first size >= switchMinT with <= switchCands candidates
+    int nB;
+    unsigned nRows, nCols;
+    int four;
+    int minSegSize;
+    double thr;
+};
+
+struct MergePlan {
+    const float *fsum;          // len x nB float32 band sums (buildSegmentSpectra)
+    const unsigned *sliceOff;   // len: list region offset of every segment
+    int64_t len;
+};
+
+size_t ssgk_merge_rec_bytes(int nB, int64_t len);
+size_t ssgk_merge_ctr_bytes(void);
+int ssgk_merge_regions(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint32_t *numPasses, int64_t *numElim);
