@@ -409,10 +409,12 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     // of the next stage is that much smaller (they then sit in L2 instead of HBM).
     // singlePixelsEliminated = oldMaxSegId - seg.max() (shepseg.py:226-227)
     uint32_t afterSingles = numClumps;
+    const uint32_t *pendingLut = nullptr;
     if (numClumps > 0) {
         SSG_TRY(ssg_reserve(ctx, ctx->aux2, (size_t)len * sizeof(unsigned)));
         unsigned *compact = bufp<unsigned>(ctx->aux2);
-        SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &afterSingles, compact));
+        // (worked out here, applied by the pixel pass of the next stage)
+        SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &afterSingles, compact, &pendingLut));
         segSize = compact;
     }
     const int64_t len1 = (int64_t)afterSingles + 1;
@@ -422,7 +424,7 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     uint32_t passes = 0, alive = 0;
     SSG_TRY(ssgk_eliminate_small(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev, segSize,
                                  afterSingles, prm->minSegSize, prm->spectralThreshold, prm->fourConnected,
-                                 &numElim, &passes));
+                                 &numElim, &passes, pendingLut, len));
     SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len1, 1, &alive));
     SSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     SSG_TRY(ssg_fetch_counters(ctx));

@@ -343,7 +343,10 @@ int ssgk_eliminate_single(ssg_ctx *ctx, const void *imgDev, int dtype, int nBand
 int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, uint32_t maxSegId,
                          int minSegSize, double thr, int four, int64_t *numElim,
-                         uint32_t *numPasses);
-// sizeOutDev (optional, len entries, must not alias sizeDev): the sizes under the new numbering
+                         uint32_t *numPasses, const uint32_t *pendingLut = nullptr, int64_t lutLen = 0);
+// sizeOutDev (optional, len entries, must not alias sizeDev): the sizes under the new numbering.
+// lutOut (optional): the relabel is only worked out, *lutOut (len entries, scratch of this call)
+// maps old to new ids and the caller applies it.
 int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
-                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev = nullptr);
+                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev = nullptr,
+                 const uint32_t **lutOut = nullptr);

@@ -262,8 +262,9 @@ k_compact_sizes(const unsigned *__restrict__ segSize, const unsigned *__restrict
 }
 
 int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
-                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev)
+                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev, const uint32_t **lutOut)
 {
+    if (lutOut) *lutOut = nullptr;
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
     *numAlive = 0;
     if (len <= 0) return SSG_OK;
@@ -282,7 +283,8 @@ int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *size
     SSG_PROF_BEGIN(ctx, "k_make_lut");
     k_make_lut<<<gridFor(len, 256), 256, 0, ctx->stream>>>(flag, sizeDev, len, minSegId, lut, counters);
     SSG_LAUNCHED(ctx);
-    if (N > 0) {
+    if (lutOut) *lutOut = lut;        // the caller applies it (in a pass it makes over the labels anyway)
+    else if (N > 0) {
         SSG_PROF_BEGIN(ctx, "k_apply_lut");
         k_apply_lut<<<gridFor((N + 3) / 4, 256), 256, 0, ctx->stream>>>(segDev, N, lut);
         SSG_LAUNCHED(ctx);
@@ -300,48 +302,6 @@ int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *size
 // ====================================================================================
 // per-segment spectra (buildSegmentSpectra, shepseg.py:780-813)
 // ====================================================================================
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_band_sums(const T *__restrict__ img, int nB, int64_t N, const unsigned *__restrict__ seg,
-            unsigned long long *isum)
-{
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < N;
-    const unsigned s = valid ? seg[p] : 0u;
-    const bool use = valid && s != 0;
-    // one atomic per band per run of equal labels in the warp's 32 consecutive pixels
-    const WarpRuns run = warp_runs(s, use);
-    for (int b = 0; b < nB; b++) {
-        const int v = use ? (int)img[(size_t)b * N + p] : 0;
-        // 32 x 65535 fits; int16 goes through the unsigned add as two's complement
-        const unsigned tot = run_suffix_add((unsigned)v, run);
-        if (run.head) atomicAdd(&isum[(size_t)s * nB + b], (unsigned long long)(long long)(int)tot);
-    }
-}
-
-// integer sums -> float32 sums where that is exact; flag the segments where it is not
-template <bool SIGNED>
-__global__ void __launch_bounds__(256)
-k_finalize_sums(const unsigned long long *__restrict__ isum, const unsigned *__restrict__ segSize,
-                int nB, int64_t len, unsigned maxAbs, float *fsum, unsigned char *bigFlag,
-                unsigned long long *counters)
-{
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool big = false;
-    if (s < len) {
-        for (int b = 0; b < nB; b++) {
-            long long v = (long long)isum[(size_t)s * nB + b];
-            fsum[(size_t)s * nB + b] = (float)v;
-            if (!SIGNED) big |= (v >= (1ll << 24));
-        }
-        if (SIGNED) big = (unsigned long long)segSize[s] * maxAbs >= (1ull << 24);
-        if (s == 0) big = false;
-        bigFlag[s] = big ? 1 : 0;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, big);
-    if (lane_id() == 0 && m) atomicAdd(&counters[C_NUM_BIGSUM], (unsigned long long)__popc(m));
-}
-
 // ordered float32 chain for one (segment, band): s = RN32(s + x) in raster order.  One warp
 // per chain: the lanes fetch 32 values at a time (the next batch is in flight while the
 // current one is added), the adds themselves run in order through shuffles.
@@ -373,42 +333,170 @@ k_ordered_sums(const T *__restrict__ img, int nB, int64_t N, const unsigned *__r
     if (lane == 0) fsum[(size_t)s * nB + b] = acc;
 }
 
+// ====================================================================================
+// One pass over the pixels for everything the merge stage needs from them
+// ====================================================================================
+// Per pixel: the pending order-preserving relabel (relabelSegments after the single-pixel stage,
+// shepseg.py:615 -- applied here instead of in a pass of its own), the band sums of
+// buildSegmentSpectra (shepseg.py:780-813) as exact integers, and the pixel lists of the small
+// segments (makeSegmentLocations, shepseg.py:880-915).  A thread takes V consecutive pixels
+// with one wide load per plane, aggregates its own runs of equal labels in registers and issues
+// one atomic per run and band PAIR: two unsigned bands share a 64-bit word (32 bits each; a
+// half can only overflow in a segment of more than 2^32 / maxValue pixels, and such a segment
+// takes the ordered path below anyway, which recomputes every band).
+//   lutF[old] = new id | (1u << 31 if the segment is small, i.e. its pixels are listed)
 template <typename T>
-static int build_spectra_t(ssg_ctx *ctx, const T *img, int nB, int64_t N, const unsigned *seg,
-                           const unsigned *segSize, int64_t len)
+__device__ __forceinline__ void load4(const T *p, unsigned (&x)[4])
 {
-    unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
-    const size_t n = (size_t)len * nB;
-    SSG_TRY(ssg_reserve(ctx, ctx->isum, n * sizeof(unsigned long long)));
-    SSG_TRY(ssg_reserve(ctx, ctx->fsum, n * sizeof(float)));
-    SSG_TRY(ssg_reserve(ctx, ctx->flags, (size_t)len));
-    unsigned long long *isum = bufp<unsigned long long>(ctx->isum);
-    float *fsum = bufp<float>(ctx->fsum);
-    unsigned char *bigFlag = bufp<unsigned char>(ctx->flags);
-    SSG_CUDA(ctx, cudaMemsetAsync(isum, 0, n * sizeof(unsigned long long), ctx->stream));
-    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_BIGSUM, 0, sizeof(unsigned long long), ctx->stream));
-    SSG_PROF_BEGIN(ctx, "k_band_sums");
-    k_band_sums<T><<<gridFor(N, 256), 256, 0, ctx->stream>>>(img, nB, N, seg, isum);
-    SSG_LAUNCHED(ctx);
-    constexpr bool isSigned = std::is_signed<T>::value;
-    const unsigned maxAbs = sizeof(T) == 1 ? 255u : 32768u;
-    SSG_PROF_BEGIN(ctx, "k_finalize_sums");
-    k_finalize_sums<isSigned><<<gridFor(len, 256), 256, 0, ctx->stream>>>(isum, segSize, nB, len, maxAbs, fsum, bigFlag, counters);
-    SSG_LAUNCHED(ctx);
-    SSG_TRY(ssg_fetch_counters(ctx));
-    if (ctx->hostCounters[C_NUM_BIGSUM] > 0) {
-        const unsigned *pixSorted = nullptr, *keysSorted = nullptr, *runStart = nullptr;
-        int64_t M = 0;
-        unsigned numRuns = 0;
-        SSG_TRY(ssgk_group_pixels(ctx, seg, N, bigFlag, &pixSorted, &keysSorted, &runStart, &M, &numRuns));
-        if (M > 0) {
-            SSG_PROF_BEGIN(ctx, "k_ordered_sums");
-            k_ordered_sums<T><<<gridFor((int64_t)numRuns * nB * 32, 128), 128, 0, ctx->stream>>>(
-                img, nB, N, pixSorted, keysSorted, runStart, numRuns, M, fsum);
-            SSG_LAUNCHED(ctx);
+    if constexpr (sizeof(T) == 2) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[i] = (unsigned)(int)e[i];      // sign-extended for int16
+    } else {
+        const unsigned r = __ldg(reinterpret_cast<const unsigned *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[i] = (unsigned)(int)e[i];
+    }
+}
+
+template <typename T, bool PACKED>
+__device__ __forceinline__ void add_band_pair(unsigned long long *isum, int NP, int nB, int j, unsigned id,
+                                              unsigned a, unsigned b)
+{
+    if (PACKED) atomicAdd(&isum[(size_t)id * NP + j], (unsigned long long)a | ((unsigned long long)b << 32));
+    else {      // signed values: one 64-bit sum per band (a, b are sign-extended 32-bit partial sums)
+        atomicAdd(&isum[(size_t)id * NP + 2 * j], (unsigned long long)(long long)(int)a);
+        if (2 * j + 1 < nB) atomicAdd(&isum[(size_t)id * NP + 2 * j + 1], (unsigned long long)(long long)(int)b);
+    }
+}
+
+template <typename T, bool PACKED>
+__global__ void __launch_bounds__(256)
+k_pixel_pass(const T *__restrict__ img, int nB, int64_t N, unsigned *seg, const unsigned *__restrict__ lutF,
+             int writeSeg, int vec, unsigned long long *isum, const unsigned *__restrict__ sliceOff, unsigned *fill,
+             unsigned *pix)
+{
+    const int NP = PACKED ? (nB + 1) / 2 : nB;      // words per segment in isum
+    const int nPairs = (nB + 1) / 2;
+    const int64_t nGroups = (N + 3) / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p0 = g * 4;
+        if (vec && p0 + 4 <= N) {
+            const uint4 o = *reinterpret_cast<const uint4 *>(seg + p0);
+            unsigned s[4];
+            s[0] = __ldg(lutF + o.x); s[1] = __ldg(lutF + o.y); s[2] = __ldg(lutF + o.z); s[3] = __ldg(lutF + o.w);
+            if (writeSeg)
+                *reinterpret_cast<uint4 *>(seg + p0) = make_uint4(s[0] & 0x7fffffffu, s[1] & 0x7fffffffu,
+                                                                  s[2] & 0x7fffffffu, s[3] & 0x7fffffffu);
+            // runs of equal labels among my four pixels
+            bool last[4];
+            last[0] = s[1] != s[0]; last[1] = s[2] != s[1]; last[2] = s[3] != s[2]; last[3] = true;
+            // pixel lists of the small segments: one slot claim per run (any order: sorted afterwards)
+            if ((s[0] | s[1] | s[2] | s[3]) >> 31) {
+                unsigned base = 0, pos = 0;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const bool head = v == 0 || last[v > 0 ? v - 1 : 0];
+                    const unsigned id = s[v] & 0x7fffffffu;
+                    if (head) {
+                        pos = 0;
+                        if (s[v] >> 31) {
+                            unsigned n = 1;
+#pragma unroll
+                            for (int w = v; w < 3; w++) {
+                                bool cont = true;
+#pragma unroll
+                                for (int z = v; z <= w; z++) cont = cont && !last[z];
+                                n += cont ? 1u : 0u;
+                            }
+                            base = atomicAdd(&fill[id], n) + __ldg(sliceOff + id);
+                        }
+                    }
+                    if (s[v] >> 31) pix[base + pos] = (unsigned)(p0 + v);
+                    pos++;
+                }
+            }
+            // band sums: one atomic per run and band pair
+            for (int j = 0; j < nPairs; j++) {
+                unsigned xa[4], xb[4];
+                load4<T>(img + (size_t)(2 * j) * N + p0, xa);
+                if (2 * j + 1 < nB) load4<T>(img + (size_t)(2 * j + 1) * N + p0, xb);
+                else { xb[0] = xb[1] = xb[2] = xb[3] = 0; }
+                unsigned a = 0, b = 0;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    a += xa[v]; b += xb[v];
+                    if (last[v]) {
+                        const unsigned id = s[v] & 0x7fffffffu;
+                        if (id != 0) add_band_pair<T, PACKED>(isum, NP, nB, j, id, a, b);
+                        a = 0; b = 0;
+                    }
+                }
+            }
+        } else {
+            for (int v = 0; v < 4 && p0 + v < N; v++) {
+                const int64_t p = p0 + v;
+                const unsigned sv = __ldg(lutF + seg[p]);
+                const unsigned id = sv & 0x7fffffffu;
+                if (writeSeg) seg[p] = id;
+                if (id == 0) continue;
+                if (sv >> 31) pix[__ldg(sliceOff + id) + atomicAdd(&fill[id], 1u)] = (unsigned)p;
+                for (int j = 0; j < nPairs; j++) {
+                    const unsigned a = (unsigned)(int)img[(size_t)(2 * j) * N + p];
+                    const unsigned b = 2 * j + 1 < nB ? (unsigned)(int)img[(size_t)(2 * j + 1) * N + p] : 0u;
+                    add_band_pair<T, PACKED>(isum, NP, nB, j, id, a, b);
+                }
+            }
         }
     }
-    return SSG_OK;
+}
+
+// integer sums -> float32 sums where that is exact; flag the segments where it is not
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_finalize_sums2(const unsigned long long *__restrict__ isum, const unsigned *__restrict__ segSize,
+                 int nB, int64_t len, unsigned maxAbs, float *fsum, unsigned char *bigFlag,
+                 unsigned long long *counters)
+{
+    const int NP = PACKED ? (nB + 1) / 2 : nB;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool big = false;
+    if (s < len) {
+        for (int b = 0; b < nB; b++) {
+            long long v;
+            if (PACKED) {
+                const unsigned long long w = isum[(size_t)s * NP + b / 2];
+                v = (long long)((b & 1) ? (w >> 32) : (w & 0xffffffffull));
+            } else {
+                v = (long long)isum[(size_t)s * NP + b];
+            }
+            fsum[(size_t)s * nB + b] = (float)v;
+            if (PACKED) big |= (v >= (1ll << 24));
+        }
+        // packed halves are exact while size * maxValue < 2^32; signed sums may cancel, so there the
+        // bound on the running sum decides
+        if (PACKED) big |= (unsigned long long)segSize[s] * maxAbs >= (1ull << 32);
+        else big = (unsigned long long)segSize[s] * maxAbs >= (1ull << 24);
+        if (s == 0) big = false;
+        bigFlag[s] = big ? 1 : 0;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    if (lane_id() == 0 && m) atomicAdd(&counters[C_NUM_BIGSUM], (unsigned long long)__popc(m));
+}
+
+// lutF[i] = (lut ? lut[i] : i) | small flag of the new id
+__global__ void __launch_bounds__(256)
+k_flag_lut(const unsigned *__restrict__ lut, int64_t n, const unsigned *__restrict__ sliceLen, int64_t len,
+           unsigned *lutF)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned v = lut ? lut[i] : (unsigned)i;
+    unsigned f = 0;
+    if (v != 0 && (int64_t)v < len && sliceLen[v] != 0) f = 0x80000000u;
+    lutF[i] = v | f;
 }
 
 // ====================================================================================
@@ -488,19 +576,6 @@ k_list_init(const unsigned *__restrict__ off, const unsigned *__restrict__ small
     mergeTo[s] = 0;
     pendHead[s] = 0;
     fill[s] = 0;
-}
-
-__global__ void __launch_bounds__(256)
-k_list_fill(const unsigned *__restrict__ seg, int64_t N, const unsigned *__restrict__ sliceOff,
-            const unsigned *__restrict__ sliceLen, unsigned *fill, unsigned *pix)
-{
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const unsigned s = seg[p];
-    if (s == 0) return;
-    if (sliceLen[s] == 0) return;
-    const unsigned slot = atomicAdd(&fill[s], 1u);
-    pix[sliceOff[s] + slot] = (unsigned)p;
 }
 
 // slots were claimed in arbitrary order: put every list back into raster order
@@ -1071,21 +1146,34 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses, i
     return SSG_OK;
 }
 
+// the pending relabel applied on its own (the paths on which the pixel pass does not run)
+static int apply_pending_lut(ssg_ctx *ctx, unsigned *seg, int64_t N, const unsigned *pendingLut)
+{
+    if (!pendingLut || N == 0) return SSG_OK;
+    SSG_PROF_BEGIN(ctx, "k_apply_lut");
+    k_apply_lut<<<gridFor((N + 3) / 4, 256), 256, 0, ctx->stream>>>(seg, N, pendingLut);
+    SSG_LAUNCHED(ctx);
+    return SSG_OK;
+}
+
+// pendingLut (optional, lutLen entries): an order-preserving relabel of `seg` that has been worked
+// out but not applied yet (segSize, maxSegId and everything else refer to the NEW ids); it is
+// applied by the pixel pass of this stage, which reads and writes every label anyway.
 template <typename T>
 static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, int64_t nCols,
                              unsigned *seg, unsigned *segSize, uint32_t maxSegId, int minSegSize,
-                             double thr, int four, int64_t *numElim, uint32_t *numPasses)
+                             double thr, int four, int64_t *numElim, uint32_t *numPasses,
+                             const unsigned *pendingLut, int64_t lutLen)
 {
     const int64_t N = nRows * nCols;
     const int64_t len = (int64_t)maxSegId + 1;
     *numElim = 0;
     *numPasses = 0;
-    if (N == 0 || minSegSize <= 1) return SSG_OK;   // the targetSize loop never runs (shepseg.py:970)
+    if (N == 0 || minSegSize <= 1)      // the targetSize loop never runs (shepseg.py:970)
+        return apply_pending_lut(ctx, seg, N, pendingLut);
     if (minSegSize > SMALL_MAX_MINSEG)
         SSG_FAIL(ctx, SSG_ERR_ARG, "minSegmentSize=%d is above the supported maximum of %d", minSegSize, SMALL_MAX_MINSEG);
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
-
-    SSG_TRY(build_spectra_t<T>(ctx, img, nB, N, seg, segSize, len));
 
     // census of the small segments: listed sizes (-> slice offsets), 0/1 flags (-> rank among the
     // small segments) and the size histogram (-> buckets); the three scans share one scratch
@@ -1117,7 +1205,8 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
     SSG_TRY(ssg_fetch_counters(ctx));
     const size_t numSmall = (size_t)ctx->hostCounters[C_NUM_SMALLSEG];
     const size_t numSmallPix = (size_t)ctx->hostCounters[C_NUM_SMALLPIX];
-    if (numSmall == 0) return SSG_OK;   // nothing can be a candidate, now or later
+    if (numSmall == 0)      // nothing can be a candidate, now or later
+        return apply_pending_lut(ctx, seg, N, pendingLut);
 
     // Pixel lists.  By default every small segment gets a region of minSegSize-1 entries of its
     // own: a list only ever grows by appending the lists of merged sources, and it cannot outgrow
@@ -1167,12 +1256,56 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
         regions ? (unsigned)(minSegSize - 1) : 0u, sliceOff, sliceLen, bufp<unsigned>(ctx->nextChunk),
         bufp<unsigned>(ctx->tailChunk), bufp<unsigned>(ctx->mergeTo), bufp<unsigned>(ctx->pendHead), fill);
     SSG_LAUNCHED(ctx);
-    SSG_PROF_BEGIN(ctx, "k_list_fill");
-    k_list_fill<<<gridFor(N, 256), 256, 0, ctx->stream>>>(seg, N, sliceOff, sliceLen, fill, pix);
-    SSG_LAUNCHED(ctx);
+    // the one pass over the pixels: pending relabel + integer band sums + pixel lists
+    {
+        constexpr bool packed = !std::is_signed<T>::value;
+        const int NP = packed ? (nB + 1) / 2 : nB;
+        const size_t nSum = (size_t)len * NP;
+        SSG_TRY(ssg_reserve(ctx, ctx->isum, nSum * sizeof(unsigned long long)));
+        SSG_TRY(ssg_reserve(ctx, ctx->fsum, (size_t)len * nB * sizeof(float)));
+        SSG_TRY(ssg_reserve(ctx, ctx->flags, (size_t)len));
+        const int64_t nLut = pendingLut ? lutLen : len;
+        SSG_TRY(ssg_reserve(ctx, ctx->sortVals0, (size_t)nLut * sizeof(unsigned)));
+        unsigned *lutF = bufp<unsigned>(ctx->sortVals0);
+        unsigned long long *isum = bufp<unsigned long long>(ctx->isum);
+        float *fsum = bufp<float>(ctx->fsum);
+        unsigned char *bigFlag = bufp<unsigned char>(ctx->flags);
+        SSG_CUDA(ctx, cudaMemsetAsync(isum, 0, nSum * sizeof(unsigned long long), ctx->stream));
+        SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_BIGSUM, 0, sizeof(unsigned long long), ctx->stream));
+        SSG_PROF_BEGIN(ctx, "k_flag_lut");
+        k_flag_lut<<<gridFor(nLut, 256), 256, 0, ctx->stream>>>(pendingLut, nLut, sliceLen, len, lutF);
+        SSG_LAUNCHED(ctx);
+        // wide loads need every band plane and the label raster 16 / 8 / 4-byte aligned
+        const int vec = (N % 4 == 0) && ((uintptr_t)seg % 16 == 0) && ((uintptr_t)img % 8 == 0);
+        int64_t blocks = ((N + 3) / 4 + 255) / 256;
+        if (blocks > (int64_t)ctx->numSMs * 16) blocks = (int64_t)ctx->numSMs * 16;
+        SSG_PROF_BEGIN(ctx, "k_pixel_pass");
+        k_pixel_pass<T, packed><<<(unsigned)blocks, 256, 0, ctx->stream>>>(img, nB, N, seg, lutF, pendingLut != nullptr, vec,
+                                                                         isum, sliceOff, fill, pix);
+        SSG_LAUNCHED(ctx);
+        const unsigned maxAbs = sizeof(T) == 1 ? 255u : (packed ? 65535u : 32768u);
+        SSG_PROF_BEGIN(ctx, "k_finalize_sums");
+        k_finalize_sums2<packed><<<gridFor(len, 256), 256, 0, ctx->stream>>>(isum, segSize, nB, len, maxAbs, fsum, bigFlag, counters);
+        SSG_LAUNCHED(ctx);
+    }
     SSG_PROF_BEGIN(ctx, "k_list_sort");
     k_list_sort<<<gridFor(len, 128), 128, 0, ctx->stream>>>(sliceOff, sliceLen, len, pix);
     SSG_LAUNCHED(ctx);
+
+    SSG_TRY(ssg_fetch_counters(ctx));
+    if (ctx->hostCounters[C_NUM_BIGSUM] > 0) {
+        // float32 sums that are not exact integers: re-accumulated in raster order (shepseg.py:805-811)
+        const unsigned *pixSorted = nullptr, *keysSorted = nullptr, *runStart = nullptr;
+        int64_t M = 0;
+        unsigned numRuns = 0;
+        SSG_TRY(ssgk_group_pixels(ctx, seg, N, bufp<unsigned char>(ctx->flags), &pixSorted, &keysSorted, &runStart, &M, &numRuns));
+        if (M > 0) {
+            SSG_PROF_BEGIN(ctx, "k_ordered_sums");
+            k_ordered_sums<T><<<gridFor((int64_t)numRuns * nB * 32, 128), 128, 0, ctx->stream>>>(
+                img, nB, N, pixSorted, keysSorted, runStart, numRuns, M, bufp<float>(ctx->fsum));
+            SSG_LAUNCHED(ctx);
+        }
+    }
 
     if (regions && !getenv("SSG_SMALL_LEGACY")) {
         // region mode: the passes of merge.cu (32-byte segment records, per-size candidate lists,
@@ -1248,12 +1381,13 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
 
 int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, uint32_t maxSegId,
-                         int minSegSize, double thr, int four, int64_t *numElim, uint32_t *numPasses)
+                         int minSegSize, double thr, int four, int64_t *numElim, uint32_t *numPasses,
+                         const uint32_t *pendingLut, int64_t lutLen)
 {
     switch (dtype) {
-    case SSG_U8: return eliminate_small_t<uint8_t>(ctx, (const uint8_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, maxSegId, minSegSize, thr, four, numElim, numPasses);
-    case SSG_U16: return eliminate_small_t<uint16_t>(ctx, (const uint16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, maxSegId, minSegSize, thr, four, numElim, numPasses);
-    case SSG_I16: return eliminate_small_t<int16_t>(ctx, (const int16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, maxSegId, minSegSize, thr, four, numElim, numPasses);
+    case SSG_U8: return eliminate_small_t<uint8_t>(ctx, (const uint8_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, maxSegId, minSegSize, thr, four, numElim, numPasses, pendingLut, lutLen);
+    case SSG_U16: return eliminate_small_t<uint16_t>(ctx, (const uint16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, maxSegId, minSegSize, thr, four, numElim, numPasses, pendingLut, lutLen);
+    case SSG_I16: return eliminate_small_t<int16_t>(ctx, (const int16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, maxSegId, minSegSize, thr, four, numElim, numPasses, pendingLut, lutLen);
     default: SSG_FAIL(ctx, SSG_ERR_ARG, "unsupported dtype code %d", dtype);
     }
 }

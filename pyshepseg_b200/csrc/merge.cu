@@ -496,7 +496,7 @@ static int run_merge_t(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint
     st.switchCands = 0;
     st.switchMinT = 2;
     if (tail) {
-        st.switchCands = 768;       // measured: below this a 16-CTA cluster finishes a phase sooner than the grid
+        st.switchCands = 320;       // measured (profiles/r2_merge.md): below this a 16-CTA cluster finishes a pass sooner than the grid
         if (const char *e = getenv("SSG_MERGE_SWITCH")) st.switchCands = (unsigned)atoi(e);
         if (const char *e = getenv("SSG_MERGE_SWITCH_T")) st.switchMinT = (unsigned)atoi(e);
         if (st.switchCands == 0) tail = false;
