@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SSG_ABI_VERSION 1
+#define SSG_ABI_VERSION 2
 
 /* image element types (numpy dtypes the reference is used with) */
 #define SSG_U8 0
@@ -124,7 +124,21 @@ typedef struct ssg_tile_params {
     int fourConnected;
     int minSegSize;
     double spectralThreshold;
+    /* Optional, for tiles that will be stitched (all zero / NULL otherwise): the final relabel of
+     * the segmentation touches every pixel anyway, so it also fills the per-segment existence
+     * tables that ssg_tile_tables_device needs (crossesMidline, tiling.py:1271-1306, and the
+     * bounding-box corner test of relabelSegments, tiling.py:1255-1265) and the stitch does not
+     * have to read the labels again.  [trimTop,trimBottom) x [trimLeft,trimRight) is the trimmed
+     * window (tiling.py:997-1022), stripRows / stripCols the overlap with the upper / left
+     * neighbour (0 without one).  extentsDev: device memory for SSG_EXTENT_TABLES byte tables of
+     * extentsCap entries each; used only if the tile ends up with fewer than extentsCap ids. */
+    int64_t trimTop, trimBottom, trimLeft, trimRight;
+    int64_t stripRows, stripCols;
+    uint8_t *extentsDev;
+    int64_t extentsCap;
 } ssg_tile_params;
+
+#define SSG_EXTENT_TABLES 10
 
 typedef struct ssg_tile_result {
     uint32_t numClumps;             /* ids after clump (shepseg.py:214) */
@@ -135,6 +149,8 @@ typedef struct ssg_tile_result {
     uint32_t numSinglePixelRounds;
     uint32_t numSmallPasses;
     float msAssign, msClump, msSingle, msSmall, msTotal; /* device time of each stage */
+    uint32_t extentsDone;           /* 1: the tables at ssg_tile_params.extentsDev are filled ... */
+    uint32_t extentsStride;         /* ... table i starts at extentsDev + i * extentsStride */
 } ssg_tile_result;
 
 /* host image in, host labels out (segOut may be NULL: labels stay resident on the device
@@ -199,11 +215,15 @@ typedef struct ssg_tile_tables {
  * resident label raster), or NULL on the first tile row / column.  [top,bottom) x
  * [left,right) is the trimmed window (tiling.py:997-1022).  maxIdHint is the largest label of
  * the tile when the caller knows it (ssg_tile_result.numSegments), 0 to have it searched.
+ * extentsDev / extentsStride: the existence tables the segmentation of this tile filled
+ * (ssg_tile_result.extentsDone, for the same window and overlaps), or NULL / 0 to have them
+ * computed here from the labels.
  * Results stay in the context until the next call; sizes come back in *out. */
 int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
                            int64_t overlap, const uint32_t *topBDev, int64_t topBStride,
                            const uint32_t *leftBDev, int64_t leftBStride, int64_t top,
                            int64_t bottom, int64_t left, int64_t right, uint32_t maxIdHint,
+                           const uint8_t *extentsDev, int64_t extentsStride,
                            ssg_tile_tables *out);
 /* rank[maxId+1] (1-based among the numbered segments, 0 otherwise), flags[maxId+1]
  * (SSG_SEG_*), pairKeys[numPairs] ascending, pairCounts[numPairs]; host buffers. */

@@ -23,6 +23,8 @@ DTYPE_CODES = {
 }
 SSG_MAX_BANDS = 16
 SSG_MAX_CLUSTERS = 1024
+SSG_EXTENT_TABLES = 10
+ABI_VERSION = 2
 
 SEG_PRESENT, SEG_NUMBERED, SEG_KEYTOP, SEG_KEYLEFT, SEG_INTRIM = 1, 2, 4, 8, 16
 PAIR_LEFT = 1 << 63
@@ -37,7 +39,10 @@ class TileParams(ctypes.Structure):
         ('nRows', ctypes.c_int64), ('nCols', ctypes.c_int64),
         ('centres', ctypes.c_void_p), ('k', ctypes.c_int), ('hasNull', ctypes.c_int),
         ('nullVal', ctypes.c_double), ('fourConnected', ctypes.c_int),
-        ('minSegSize', ctypes.c_int), ('spectralThreshold', ctypes.c_double)]
+        ('minSegSize', ctypes.c_int), ('spectralThreshold', ctypes.c_double),
+        ('trimTop', ctypes.c_int64), ('trimBottom', ctypes.c_int64), ('trimLeft', ctypes.c_int64),
+        ('trimRight', ctypes.c_int64), ('stripRows', ctypes.c_int64), ('stripCols', ctypes.c_int64),
+        ('extentsDev', ctypes.c_void_p), ('extentsCap', ctypes.c_int64)]
 
 
 class TileResult(ctypes.Structure):
@@ -46,7 +51,8 @@ class TileResult(ctypes.Structure):
         ('smallSegmentsEliminated', ctypes.c_int64), ('numOversized', ctypes.c_uint32),
         ('numSinglePixelRounds', ctypes.c_uint32), ('numSmallPasses', ctypes.c_uint32),
         ('msAssign', ctypes.c_float), ('msClump', ctypes.c_float), ('msSingle', ctypes.c_float),
-        ('msSmall', ctypes.c_float), ('msTotal', ctypes.c_float)]
+        ('msSmall', ctypes.c_float), ('msTotal', ctypes.c_float),
+        ('extentsDone', ctypes.c_uint32), ('extentsStride', ctypes.c_uint32)]
 
 
 class TileTables(ctypes.Structure):
@@ -85,7 +91,7 @@ SIGNATURES = {
     'ssg_download_labels': (_i, [_vp, _vp]),
     'ssg_resident_labels': (_vp, [_vp]),
     'ssg_tile_tables_device': (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64,
-        _i64, _u32, _c.POINTER(TileTables)]),
+        _i64, _u32, _vp, _i64, _c.POINTER(TileTables)]),
     'ssg_tile_tables_fetch': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'ssg_apply_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _u32, _i64, _i64, _i64, _i64, _vp, _i64,
         _vp, _i64]),

@@ -425,7 +425,13 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     SSG_TRY(ssgk_eliminate_small(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev, segSize,
                                  afterSingles, prm->minSegSize, prm->spectralThreshold, prm->fourConnected,
                                  &numElim, &passes, pendingLut, len));
-    SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len1, 1, &alive));
+    // the final relabel; for a tile that will be stitched the same pass fills the existence tables
+    const uint32_t *finalLut = nullptr;
+    SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len1, 1, &alive, nullptr, &finalLut));
+    bool extDone = false;
+    uint32_t extStride = 0;
+    SSG_TRY(ssgk_apply_lut_extents(ctx, segDev, prm->nRows, prm->nCols, finalLut, alive, prm, &extStride, &extDone));
+    if (!extDone) SSG_TRY(ssgk_apply_lut(ctx, segDev, N, finalLut));
     SSG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     SSG_TRY(ssg_fetch_counters(ctx));
 
@@ -436,6 +442,8 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
     res->smallSegmentsEliminated = numElim;
     res->numSinglePixelRounds = rounds;
     res->numSmallPasses = passes;
+    res->extentsDone = extDone ? 1u : 0u;
+    res->extentsStride = extStride;
     cudaEventElapsedTime(&res->msAssign, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&res->msClump, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&res->msSingle, ctx->ev[2], ctx->ev[3]);

@@ -326,6 +326,9 @@ int ssgk_group_pixels(ssg_ctx *ctx, const unsigned *segDev, int64_t N, const uns
                       const unsigned **runStart, int64_t *M, unsigned *numRuns);
 
 // stage entry points implemented in the other translation units ------------------------
+int ssgk_apply_lut_extents(ssg_ctx *ctx, unsigned *seg, int64_t ysize, int64_t xsize, const unsigned *lut,
+                           uint32_t numIds, const ssg_tile_params *prm, uint32_t *stride, bool *done);
+int ssgk_apply_lut(ssg_ctx *ctx, unsigned *seg, int64_t N, const unsigned *lut);
 int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t N,
                 const double *centresHost, int k, int hasNull, double nullVal, int32_t *outDev);
 // singlesOut (optional): receives the number of single-pixel clumps whose pixels were listed in

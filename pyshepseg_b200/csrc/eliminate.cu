@@ -1146,6 +1146,15 @@ static int run_small_passes(ssg_ctx *ctx, SmallState &st, uint32_t *numPasses, i
     return SSG_OK;
 }
 
+int ssgk_apply_lut(ssg_ctx *ctx, unsigned *seg, int64_t N, const unsigned *lut)
+{
+    if (N == 0) return SSG_OK;
+    SSG_PROF_BEGIN(ctx, "k_apply_lut");
+    k_apply_lut<<<gridFor((N + 3) / 4, 256), 256, 0, ctx->stream>>>(seg, N, lut);
+    SSG_LAUNCHED(ctx);
+    return SSG_OK;
+}
+
 // the pending relabel applied on its own (the paths on which the pixel pass does not run)
 static int apply_pending_lut(ssg_ctx *ctx, unsigned *seg, int64_t N, const unsigned *pendingLut)
 {

@@ -59,21 +59,11 @@ k_tile_max(const unsigned *__restrict__ tile, int64_t N, unsigned long long *cou
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, unsigned topRows,
-               unsigned leftCols, unsigned top, unsigned bottom, unsigned left, unsigned right,
-               StitchTables tb)
+// what one run of equal labels inside one raster row (row r, columns c..cEnd) says about its segment
+__device__ __forceinline__ void extents_mark(const StitchTables &tb, unsigned s, unsigned r, unsigned c, unsigned cEnd,
+                                             unsigned topRows, unsigned leftCols, unsigned top, unsigned bottom,
+                                             unsigned left, unsigned right)
 {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = p < ysize * xsize;
-    const unsigned s = valid ? tile[p] : 0u;
-    const bool use = valid && s != 0;
-    const unsigned r = (unsigned)(p / xsize), c = (unsigned)(p % xsize);
-    // a run of equal labels inside one raster row: its head lane knows the row and the first and
-    // last column, and speaks for the whole run
-    const WarpRuns run = warp_runs(s, use, c == 0);
-    if (!run.head) return;
-    const unsigned cEnd = c + run.len - 1u;
     const bool rowInTrim = r >= top && r < bottom;
     const bool touchesTrim = rowInTrim && cEnd >= left && c < right;
     const bool allInTrim = rowInTrim && c >= left && cEnd < right;
@@ -93,6 +83,50 @@ k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, 
         const unsigned mid = leftCols / 2;
         if (c < mid) tb.leftA[s] = 1;
         if (cEnd >= mid) tb.leftB[s] = 1;      // (c < leftCols and cEnd >= mid: a pixel in [mid, leftCols))
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_extents(const unsigned *__restrict__ tile, int64_t ysize, int64_t xsize, unsigned topRows,
+               unsigned leftCols, unsigned top, unsigned bottom, unsigned left, unsigned right,
+               StitchTables tb)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < ysize * xsize;
+    const unsigned s = valid ? tile[p] : 0u;
+    const bool use = valid && s != 0;
+    const unsigned r = (unsigned)(p / xsize), c = (unsigned)(p % xsize);
+    // a run of equal labels inside one raster row: its head lane knows the row and the first and
+    // last column, and speaks for the whole run
+    const WarpRuns run = warp_runs(s, use, c == 0);
+    if (!run.head) return;
+    extents_mark(tb, s, r, c, c + run.len - 1u, topRows, leftCols, top, bottom, left, right);
+}
+
+// seg = lut[seg] (the final order-preserving relabel of a tile, shepseg.py:739-777) and, in the
+// same pass, the existence tables of the new ids.  A thread takes four consecutive pixels of a
+// row (xsize is a multiple of 4 on this path) and speaks for its own runs.
+__global__ void __launch_bounds__(256)
+k_apply_lut_extents(unsigned *seg, int64_t ysize, int64_t xsize, const unsigned *__restrict__ lut, unsigned topRows,
+                    unsigned leftCols, unsigned top, unsigned bottom, unsigned left, unsigned right, StitchTables tb)
+{
+    const int64_t nGroups = ysize * xsize / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p0 = g * 4;
+        uint4 v = *reinterpret_cast<const uint4 *>(seg + p0);
+        v.x = __ldg(lut + v.x); v.y = __ldg(lut + v.y); v.z = __ldg(lut + v.z); v.w = __ldg(lut + v.w);
+        *reinterpret_cast<uint4 *>(seg + p0) = v;
+        const unsigned r = (unsigned)(p0 / xsize), c0 = (unsigned)(p0 - (int64_t)r * xsize);
+        const unsigned s[4] = {v.x, v.y, v.z, v.w};
+        unsigned start = 0;
+#pragma unroll
+        for (unsigned i = 0; i < 4; i++) {
+            const bool last = i == 3 || s[i + 1 < 4 ? i + 1 : 3] != s[i];
+            if (last) {
+                if (s[i] != 0) extents_mark(tb, s[i], r, c0 + start, c0 + i, topRows, leftCols, top, bottom, left, right);
+                start = i + 1;
+            }
+        }
     }
 }
 
@@ -154,20 +188,57 @@ k_collect_pairs(const unsigned *__restrict__ tile, int64_t xsize, int64_t stripR
     if (hit) keys[slot] = key;
 }
 
-static int reserveTables(ssg_ctx *ctx, int64_t len, StitchTables &tb, unsigned **numbered,
-                         unsigned **excl, unsigned **rank, unsigned char **flags)
+static void tablesAt(unsigned char *base, size_t n, StitchTables &tb)
 {
-    const size_t n = ((size_t)len + 15) & ~(size_t)15;
-    SSG_TRY(ssg_reserve(ctx, ctx->stitch0, n * STITCH_TABLES));
-    SSG_TRY(ssg_reserve(ctx, ctx->stitch1, (size_t)len * 3 * sizeof(unsigned) + (size_t)len));
-    unsigned char *base = bufp<unsigned char>(ctx->stitch0);
     tb.interior = base; tb.margin = base + n; tb.leftOf = base + 2 * n; tb.above = base + 3 * n;
     tb.ltRight = base + 4 * n; tb.ltBottom = base + 5 * n; tb.topA = base + 6 * n; tb.topB = base + 7 * n;
     tb.leftA = base + 8 * n; tb.leftB = base + 9 * n;
+}
+
+// given: the tables filled by the segmentation (ssg_tile_params.extentsDev), or nullptr
+static int reserveTables(ssg_ctx *ctx, int64_t len, StitchTables &tb, unsigned **numbered,
+                         unsigned **excl, unsigned **rank, unsigned char **flags,
+                         const unsigned char *given, size_t givenStride)
+{
+    const size_t n = ((size_t)len + 15) & ~(size_t)15;
+    SSG_TRY(ssg_reserve(ctx, ctx->stitch1, (size_t)len * 3 * sizeof(unsigned) + (size_t)len));
+    if (given) tablesAt(const_cast<unsigned char *>(given), givenStride, tb);
+    else {
+        SSG_TRY(ssg_reserve(ctx, ctx->stitch0, n * STITCH_TABLES));
+        unsigned char *base = bufp<unsigned char>(ctx->stitch0);
+        tablesAt(base, n, tb);
+        SSG_CUDA(ctx, cudaMemsetAsync(base, 0, n * STITCH_TABLES, ctx->stream));
+    }
     unsigned *b1 = bufp<unsigned>(ctx->stitch1);
     *numbered = b1; *excl = b1 + len; *rank = b1 + 2 * len;
     *flags = reinterpret_cast<unsigned char *>(b1 + 3 * len);
-    SSG_CUDA(ctx, cudaMemsetAsync(base, 0, n * STITCH_TABLES, ctx->stream));
+    return SSG_OK;
+}
+
+// the final relabel of a tile fused with the existence tables (see ssg_tile_params): returns
+// false in *done (and does nothing) when the tables do not fit or the vector path does not apply
+int ssgk_apply_lut_extents(ssg_ctx *ctx, unsigned *seg, int64_t ysize, int64_t xsize, const unsigned *lut,
+                           uint32_t numIds, const ssg_tile_params *prm, uint32_t *stride, bool *done)
+{
+    *done = false;
+    *stride = 0;
+    const int64_t len = (int64_t)numIds + 1;
+    const size_t n = ((size_t)len + 15) & ~(size_t)15;
+    if (!prm->extentsDev || (int64_t)n > prm->extentsCap || xsize % 4 != 0 || ((uintptr_t)seg % 16) != 0 ||
+        ysize * xsize == 0)
+        return SSG_OK;
+    StitchTables tb;
+    tablesAt(prm->extentsDev, n, tb);
+    SSG_CUDA(ctx, cudaMemsetAsync(prm->extentsDev, 0, n * STITCH_TABLES, ctx->stream));
+    int64_t blocks = (ysize * xsize / 4 + 255) / 256;
+    if (blocks > (int64_t)ctx->numSMs * 16) blocks = (int64_t)ctx->numSMs * 16;
+    SSG_PROF_BEGIN(ctx, "k_apply_lut_extents");
+    k_apply_lut_extents<<<(unsigned)blocks, 256, 0, ctx->stream>>>(seg, ysize, xsize, lut, (unsigned)prm->stripRows,
+        (unsigned)prm->stripCols, (unsigned)prm->trimTop, (unsigned)prm->trimBottom, (unsigned)prm->trimLeft,
+        (unsigned)prm->trimRight, tb);
+    SSG_LAUNCHED(ctx);
+    *stride = (uint32_t)n;
+    *done = true;
     return SSG_OK;
 }
 
@@ -175,7 +246,7 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
                                       int64_t overlap, const uint32_t *topBDev, int64_t topBStride,
                                       const uint32_t *leftBDev, int64_t leftBStride, int64_t top,
                                       int64_t bottom, int64_t left, int64_t right, uint32_t maxIdHint,
-                                      ssg_tile_tables *out)
+                                      const uint8_t *extentsDev, int64_t extentsStride, ssg_tile_tables *out)
 {
     if (!ctx) return SSG_ERR_ARG;
     ctx->err.clear();
@@ -201,14 +272,17 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     StitchTables tb;
     unsigned *numbered, *excl, *rank;
     unsigned char *flags;
-    SSG_TRY(reserveTables(ctx, len, tb, &numbered, &excl, &rank, &flags));
+    if (extentsDev && extentsStride < len) SSG_FAIL(ctx, SSG_ERR_ARG, "extent tables of stride %lld for %lld ids", (long long)extentsStride, (long long)len);
+    SSG_TRY(reserveTables(ctx, len, tb, &numbered, &excl, &rank, &flags, extentsDev, (size_t)extentsStride));
     const int64_t topRows = topBDev ? (overlap < ysize ? overlap : ysize) : 0;
     const int64_t leftCols = leftBDev ? (overlap < xsize ? overlap : xsize) : 0;
-    SSG_PROF_BEGIN(ctx, "k_tile_extents");
-    k_tile_extents<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, ysize, xsize, (unsigned)topRows, (unsigned)leftCols,
-                                                            (unsigned)top, (unsigned)bottom, (unsigned)left,
-                                                            (unsigned)right, tb);
-    SSG_LAUNCHED(ctx);
+    if (!extentsDev) {
+        SSG_PROF_BEGIN(ctx, "k_tile_extents");
+        k_tile_extents<<<gridFor(N, 256), 256, 0, ctx->stream>>>(tileDev, ysize, xsize, (unsigned)topRows, (unsigned)leftCols,
+                                                                (unsigned)top, (unsigned)bottom, (unsigned)left,
+                                                                (unsigned)right, tb);
+        SSG_LAUNCHED(ctx);
+    }
     // mid = int(n / 2) of the strip's stitch axis (tiling.py:1297,1300)
     SSG_PROF_BEGIN(ctx, "k_tile_flags");
     k_tile_flags<<<gridFor(len, 256), 256, 0, ctx->stream>>>(tb, len, topBDev != nullptr, leftBDev != nullptr, flags,

@@ -578,9 +578,19 @@ class TiledSegmenter(object):
                 ctx.call('ssg_upload_image', _lib.ptr(img), _lib.DTYPE_CODES[numpy.dtype(dtype)], nB,
                     tile.ysize, tile.xsize)
                 imgDev = ctx.lib.ssg_staged_image(ctx.h)
-            tile.buf = pool.get(ctx, nPix * 4)
+            # the labels, followed by room for the per-segment existence tables of the stitch: the
+            # final relabel of the segmentation fills them while it has the labels in its hands
+            extCap = self._extentsCap(nPix)
+            tile.buf = pool.get(ctx, nPix * 4 + extCap * _lib.SSG_EXTENT_TABLES)
             prm = shepseg.makeTileParams(dtype, nB, tile.ysize, tile.xsize, self.centres,
                 self.imgNullVal, self.fourConnected, self.minSegmentSize, self.thr)
+            (prm.trimTop, prm.trimBottom, prm.trimLeft, prm.trimRight) = tileMargins(self.tileInfo, tile.col,
+                tile.row, tile.xsize, tile.ysize, self.overlapSize)
+            ov = self.overlapSize
+            prm.stripRows = 0 if (tile.row == 0 or self.simple) else min(ov, tile.ysize)
+            prm.stripCols = 0 if (tile.col == 0 or self.simple) else min(ov, tile.xsize)
+            prm.extentsDev = tile.buf[1] + nPix * 4
+            prm.extentsCap = extCap
             res = _lib.TileResult()
             ctx.call('ssg_segment_tile_device', imgDev, ctypes.byref(prm), tile.buf[1], ctypes.byref(res))
         self.mark('tile %d,%d segmented (dev %.1f ms)' % (tile.col, tile.row, res.msTotal))
@@ -591,6 +601,12 @@ class TiledSegmenter(object):
                 self.h2dBytes += nB * nPix * item
             for k in self.stageMs:
                 self.stageMs[k] += getattr(res, 'ms' + k.capitalize())
+
+    @staticmethod
+    def _extentsCap(nPix):
+        """entries per existence table kept behind a tile's labels (a tile with more segments than
+        this has its tables computed by the stitch instead)"""
+        return ((nPix // 16 + 4096) + 15) // 16 * 16
 
     def _startUpload(self, state, slotIndex, order=None):
         """Stream the raster to the device in one piece (see _RasterUploader) when it is host
@@ -706,9 +722,12 @@ class TiledSegmenter(object):
             tile.ysize, self.overlapSize)
         tables = _lib.TileTables()
         with self.timings.interval('stitch_tables'):
+            res = tile.result
+            given = res is not None and res.extentsDone
             ctx.call('ssg_tile_tables_device', tile.buf[1], tile.ysize, tile.xsize, self.overlapSize,
                 topB, topStride, leftB, leftStride, top, bottom, left, right, tile.numSegments,
-                ctypes.byref(tables))
+                (tile.buf[1] + tile.ysize * tile.xsize * 4) if given else None,
+                int(res.extentsStride) if given else 0, ctypes.byref(tables))
             n = int(tables.maxId) + 1
             rank = numpy.empty(n, dtype=numpy.uint32)
             flags = numpy.empty(n, dtype=numpy.uint8)

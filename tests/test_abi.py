@@ -34,7 +34,7 @@ def test_python_binding_covers_the_header():
 
 def test_no_cpu_fallback():
     lib = _lib.load()
-    assert lib.ssg_abi_version() == 1
+    assert lib.ssg_abi_version() == 2
     if lib.ssg_device_count() == 0:
         with pytest.raises(_lib.ShepsegB200Error):
             _lib.Context(0)
