@@ -133,3 +133,33 @@ def test_memory_raster_row_band_view():
     band = rasterfile.MemoryRaster(img[:, 2:5], yoff=2, fullYsize=6)
     assert (band.ysize, band.fullYsize, band.yoff) == (3, 6, 2)
     assert rasterfile.MemoryRaster(img).fullYsize == 6
+
+
+def test_statistics_from_histogram_equal_the_reference_expressions():
+    """utils.estimateStatsFromHisto (utils.py:47-95), restated with fewer passes: same strings"""
+    def reference(hist):
+        mask = hist > 0
+        nVals = hist.sum()
+        minVal = mask.argmax()
+        maxVal = hist.shape[0] - numpy.flip(mask).argmax() - 1
+        values = numpy.arange(hist.shape[0])
+        meanVal = (values * hist).sum() / nVals
+        stdDevVal = numpy.sqrt((hist * numpy.power(values - meanVal, 2)).sum() / nVals)
+        medianVal = (hist.cumsum() >= hist.sum() / 2).nonzero()[0][0]
+        return [repr(int(minVal)), repr(int(maxVal)), repr(float(meanVal)), repr(float(stdDevVal)),
+            repr(int(numpy.argmax(hist))), repr(int(medianVal))]
+    rng = numpy.random.default_rng(1)
+    for n in (5, 1000, 200001):
+        for trial in range(3):
+            hist = rng.integers(0, 3000, n).astype(numpy.float64)
+            hist[0] = 0
+            if trial == 1:
+                hist[:n // 3] = 0
+            if trial == 2:
+                hist[-(n // 4):] = 0
+                hist[1] = 7
+            sink = rasterfile.MemorySink(4, 4)
+            tiling.estimateStatsFromHisto(sink, hist)
+            m = sink.metadata
+            assert [m['STATISTICS_' + k] for k in ('MINIMUM', 'MAXIMUM', 'MEAN', 'STDDEV', 'MODE', 'MEDIAN')] == \
+                reference(hist)
