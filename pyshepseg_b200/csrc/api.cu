@@ -67,7 +67,7 @@ void ssg_ctx_destroy(ssg_ctx *ctx)
                       &ctx->segSize, &ctx->isum, &ctx->fsum, &ctx->listOff, &ctx->nextChunk, &ctx->tailChunk,
                       &ctx->mergeTo, &ctx->pendHead, &ctx->pendNext, &ctx->candList, &ctx->targetList, &ctx->lut,
                       &ctx->flags, &ctx->blockCnt, &ctx->cubTemp, &ctx->sortKeys0, &ctx->sortKeys1, &ctx->sortVals0,
-                      &ctx->sortVals1, &ctx->emuStack, &ctx->centres, &ctx->counters, &ctx->stitch0, &ctx->stitch1,
+                      &ctx->sortVals1, &ctx->emuStack, &ctx->centres, &ctx->assignGrid, &ctx->counters, &ctx->stitch0, &ctx->stitch1,
                       &ctx->stitch2, &ctx->stitch3, &ctx->stitch4, &ctx->stitch5};
     for (DevBuf *b : bufs) if (b->p && !b->scratch) cudaFree(b->p);
     for (void *q : ctx->spills) cudaFree(q);

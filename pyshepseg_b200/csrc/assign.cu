@@ -187,6 +187,195 @@ k_assign(const T *__restrict__ img, int64_t N, const double *__restrict__ centre
     }
 }
 
+// ---- pruned assignment for few bands ---------------------------------------------------------
+// With up to four bands the band space is cut into a grid of boxes (power-of-two widths over the
+// range the centres span, one outer box on either side out to the limits of the data type) and
+// every box knows which centres can be nearest to ANY integer point inside it:
+//     U = min_j maxdist^2(box, c_j)   is an upper bound of the best distance of every such point,
+//     centre j stays  <=>  mindist^2(box, c_j) <= U (+ a float64 rounding margin),
+// since a centre farther than U from the whole box is strictly farther than the best one from
+// every point of it (ties are within the margin and stay).  A pixel then evaluates only the
+// centres of its box -- a few instead of all k -- in ascending j with the same float32 fast pass
+// and guarded float64 recheck as the full scan, so the label is still the float64 first-minimum
+// argmin over all k centres.  The table is a 64-bit mask per box (k <= 64), built on the device
+// when the centres change and kept in the context.
+
+__global__ void __launch_bounds__(256)
+k_grid_build(const double *__restrict__ centres, int k, GridGeom g, unsigned long long *__restrict__ grid, int64_t nCells)
+{
+    extern __shared__ double sc[];      // k * nB
+    for (int i = threadIdx.x; i < k * g.nB; i += blockDim.x) sc[i] = centres[i];
+    __syncthreads();
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= nCells) return;
+    double lo[4], hi[4];
+    int64_t rest = cell;
+    bool empty = false;
+    for (int b = g.nB - 1; b >= 0; b--) {
+        const int qb = (int)(rest % g.q[b]);
+        rest /= g.q[b];
+        const long long w = 1ll << g.shift[b];
+        long long a = qb == 0 ? (long long)g.tmin : (long long)g.base[b] + qb * w;
+        long long z = qb == g.q[b] - 1 ? (long long)g.tmax : (long long)g.base[b] + (qb + 1) * w - 1;
+        if (a < g.tmin) a = g.tmin;
+        if (z > g.tmax) z = g.tmax;
+        empty |= a > z;
+        lo[b] = (double)a;
+        hi[b] = (double)z;
+    }
+    if (empty) { grid[cell] = 0ull; return; }
+    double U = 1e300;
+    for (int j = 0; j < k; j++) {
+        double far2 = 0.0;
+        for (int b = 0; b < g.nB; b++) {
+            const double c = sc[j * g.nB + b];
+            const double d0 = c - lo[b], d1 = hi[b] - c;
+            const double d = fmax(fabs(d0), fabs(d1));
+            far2 += d * d;
+        }
+        U = fmin(U, far2);
+    }
+    const double limit = U * (1.0 + 1e-9) + 1e-6;
+    unsigned long long mask = 0ull;
+    for (int j = 0; j < k; j++) {
+        double near2 = 0.0;
+        for (int b = 0; b < g.nB; b++) {
+            const double c = sc[j * g.nB + b];
+            const double d = c < lo[b] ? lo[b] - c : (c > hi[b] ? c - hi[b] : 0.0);
+            near2 += d * d;
+        }
+        if (near2 <= limit) mask |= 1ull << j;
+    }
+    grid[cell] = mask;
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void load_raw(const T *p, int (&x)[V])
+{
+    constexpr int BYTES = V * (int)sizeof(T);
+    if constexpr (BYTES == 16) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (int)e[i];
+    } else if constexpr (BYTES == 8) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (int)e[i];
+    } else {
+        const unsigned r = __ldg(reinterpret_cast<const unsigned *>(p));
+        const T *e = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int i = 0; i < V; i++) x[i] = (int)e[i];
+    }
+}
+
+template <typename T, int NB, int V>
+__global__ void __launch_bounds__(256)
+k_assign_grid(const T *__restrict__ img, int64_t N, const double *__restrict__ centres, int k,
+              int hasNull, double nullVal, AssignBounds bnd, GridGeom g,
+              const unsigned long long *__restrict__ grid, int32_t *__restrict__ out)
+{
+    // rows of NB+1 floats {||c||^2, -2c}: an odd stride, so lanes that look at different centres
+    // hit different banks (lanes that look at the same one are a broadcast)
+    constexpr int CS = NB + 1 + ((NB + 1) % 2 == 0 ? 1 : 0);
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    double *cd = reinterpret_cast<double *>(smemRaw);          // k*NB
+    double *cn = cd + (size_t)k * NB;                          // k
+    float *cf = reinterpret_cast<float *>(cn + k);             // k x CS
+    for (int i = threadIdx.x; i < k * NB; i += blockDim.x) cd[i] = centres[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            s = __dadd_rn(s, __dmul_rn(cd[j * NB + b], cd[j * NB + b]));
+            cf[j * CS + 1 + b] = (float)(-2.0 * cd[j * NB + b]);
+        }
+        cn[j] = s;
+        cf[j * CS] = (float)s;
+    }
+    __syncthreads();
+
+    const int64_t nGroups = N / V;        // (the launcher takes this path only when N is a multiple of V)
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < nGroups; gi += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p0 = gi * V;
+        float x[V][NB];
+        int cellOf[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) cellOf[v] = 0;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            int t[V];
+            load_raw<T, V>(img + (size_t)b * N + p0, t);
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                x[v][b] = (float)t[v];
+                int qb = (t[v] - g.base[b]) >> g.shift[b];
+                qb = min(max(qb, 0), g.q[b] - 1);
+                cellOf[v] = cellOf[v] * g.q[b] + qb;
+            }
+        }
+        // the centres that can be nearest to any of my V (adjacent, hence similar) pixels: evaluating
+        // a centre for a pixel whose box does not list it costs a little and changes nothing
+        unsigned long long M = 0ull;
+#pragma unroll
+        for (int v = 0; v < V; v++) M |= __ldg(grid + cellOf[v]);
+
+        float best[V], second[V];
+        int idx[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) { best[v] = 3.0e38f; second[v] = 3.0e38f; idx[v] = 0; }
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            unsigned m = half == 0 ? (unsigned)M : (unsigned)(M >> 32);
+            while (m) {
+                const int j = (__ffs(m) - 1) + 32 * half;
+                m &= m - 1;
+                float c[NB + 1];
+#pragma unroll
+                for (int b = 0; b <= NB; b++) c[b] = cf[j * CS + b];
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    float acc = c[0];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) acc = fmaf(x[v][b], c[b + 1], acc);
+                    second[v] = fminf(second[v], fmaxf(acc, best[v]));
+                    const bool lt = acc < best[v];
+                    best[v] = fminf(acc, best[v]);
+                    idx[v] = lt ? j : idx[v];
+                }
+            }
+        }
+        int32_t res[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            const float gap = second[v] - best[v];
+            float absSum = 0.0f;
+#pragma unroll
+            for (int b = 0; b < NB; b++) absSum += fabsf(x[v][b]);
+            const float tol = fmaf(bnd.perAbsX, absSum, bnd.constant);
+            int lab = idx[v];
+            if (!(gap > tol)) {
+                float xv[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++) xv[b] = x[v][b];
+                lab = assign_exact<NB>(xv, cd, cn, k);
+            }
+            bool isNull = false;
+            if (hasNull) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) isNull |= ((double)x[v][b] == nullVal);
+            }
+            res[v] = isNull ? 0 : lab + 1;
+        }
+        int4 *o = reinterpret_cast<int4 *>(out + p0);
+        o[0] = make_int4(res[0], res[1], res[2], res[3]);
+        if constexpr (V == 8) o[1] = make_int4(res[4], res[5], res[6], res[7]);
+    }
+}
+
 template <typename T, int NB, int V>
 static int launch_assign(ssg_ctx *ctx, const void *img, int64_t N, const double *centresDev, int k,
                          int hasNull, double nullVal, AssignBounds bnd, int32_t *out)
@@ -267,6 +456,77 @@ int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t
     AssignBounds bnd;
     bnd.perAbsX = (float)(e32 * 2.0 * cmax * 1.001);
     bnd.constant = (float)((e32 * cnmax + margin64) * 1.001);
+    // few bands, at most 64 centres, wide loads possible: the pruned kernel
+    const bool gridOff = getenv("SSG_ASSIGN_GRID") && atoi(getenv("SSG_ASSIGN_GRID")) == 0;
+    const size_t itemSize = dtypeSize(dtype);
+    if (!gridOff && nBands <= 4 && k >= 2 && k <= 64 && N % 8 == 0 && ((uintptr_t)imgDev % 16 == 0) &&
+        ((uintptr_t)outDev % 16 == 0) && ((size_t)N * itemSize) % 16 == 0) {
+        const int tmin = dtype == SSG_I16 ? -32768 : 0;
+        const int tmax = dtype == SSG_U8 ? 255 : (dtype == SSG_U16 ? 65535 : 32767);
+        const bool same = ctx->gridDtype == dtype && ctx->gridK == k && ctx->gridGeom.nB == nBands &&
+                          ctx->gridCentres.size() == nc && memcmp(ctx->gridCentres.data(), centresHost, nc * sizeof(double)) == 0;
+        static const int cellsPerBand[5] = {0, 4096, 512, 64, 32};
+        if (!same) {
+            GridGeom g = {};
+            g.nB = nBands;
+            g.tmin = tmin; g.tmax = tmax;
+            int64_t nCells = 1;
+            for (int b = 0; b < nBands; b++) {
+                double lo = centresHost[b], hi = centresHost[b];
+                for (int j = 1; j < k; j++) {
+                    const double c = centresHost[(size_t)j * nBands + b];
+                    if (c < lo) lo = c;
+                    if (c > hi) hi = c;
+                }
+                // (centres outside the data type's range cannot make the grid wider than the data)
+                long long cmin = (long long)floor(lo < tmin ? (double)tmin : (lo > tmax ? (double)tmax : lo));
+                long long cmax = (long long)ceil(hi > tmax ? (double)tmax : (hi < tmin ? (double)tmin : hi));
+                const int q = cellsPerBand[nBands];
+                int shift = 0;
+                while (((long long)(q - 2) << shift) < cmax - cmin + 1) shift++;
+                g.q[b] = q;
+                g.shift[b] = shift;
+                g.base[b] = (int)(cmin - (1ll << shift));
+                nCells *= q;
+            }
+            SSG_TRY(ssg_reserve(ctx, ctx->assignGrid, (size_t)nCells * sizeof(unsigned long long)));
+            SSG_PROF_BEGIN(ctx, "k_grid_build");
+            k_grid_build<<<gridFor(nCells, 256), 256, nc * sizeof(double), ctx->stream>>>(centresDev, k, g,
+                bufp<unsigned long long>(ctx->assignGrid), nCells);
+            SSG_LAUNCHED(ctx);
+            ctx->gridGeom = g;
+            ctx->gridDtype = dtype;
+            ctx->gridK = k;
+            ctx->gridCentres.assign(centresHost, centresHost + nc);
+        }
+        const GridGeom g = ctx->gridGeom;
+        const size_t smem = nc * sizeof(double) + (size_t)k * sizeof(double) + (size_t)k * 6 * sizeof(float);
+        int V = 4;      // pixels per thread: 4 leaves room for twice the warps of 8 (the loop waits on shared memory)
+        if (const char *e = getenv("SSG_ASSIGN_V")) V = atoi(e) == 8 ? 8 : 4;
+        int64_t blocks = (N / V + 255) / 256;
+        if (blocks > (int64_t)ctx->numSMs * 16) blocks = (int64_t)ctx->numSMs * 16;
+        const unsigned long long *grid = bufp<unsigned long long>(ctx->assignGrid);
+        SSG_PROF_BEGIN(ctx, "k_assign_grid");
+#define GRID_CASE(T, NB)                                                                                   \
+        if (V == 8) k_assign_grid<T, NB, 8><<<(unsigned)blocks, 256, smem, ctx->stream>>>(reinterpret_cast<const T *>(imgDev), N, \
+            centresDev, k, hasNull, nullVal, bnd, g, grid, outDev);                                         \
+        else k_assign_grid<T, NB, 4><<<(unsigned)blocks, 256, smem, ctx->stream>>>(reinterpret_cast<const T *>(imgDev), N, \
+            centresDev, k, hasNull, nullVal, bnd, g, grid, outDev)
+#define GRID_NB(T)                                                           \
+        switch (nBands) {                                                    \
+        case 1: GRID_CASE(T, 1); break;                                      \
+        case 2: GRID_CASE(T, 2); break;                                      \
+        case 3: GRID_CASE(T, 3); break;                                      \
+        default: GRID_CASE(T, 4); break;                                     \
+        }
+        if (dtype == SSG_U8) { GRID_NB(uint8_t) }
+        else if (dtype == SSG_U16) { GRID_NB(uint16_t) }
+        else { GRID_NB(int16_t) }
+#undef GRID_NB
+#undef GRID_CASE
+        SSG_LAUNCHED(ctx);
+        return SSG_OK;
+    }
     switch (dtype) {
     case SSG_U8: return dispatch_nb<uint8_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);
     case SSG_U16: return dispatch_nb<uint16_t>(ctx, imgDev, nBands, N, centresDev, k, hasNull, nullVal, bnd, outDev);

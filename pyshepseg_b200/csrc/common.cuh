@@ -15,6 +15,13 @@
 #define SSG_NIL 0xFFFFFFFFu          // "no pixel / no root / no chunk"
 #define SSG_MAX_CLUMP_SIZE 10000u    // shepseg.py:481
 
+// geometry of the pruning grid of the assignment kernel (assign.cu)
+struct GridGeom {
+    int nB;
+    int base[4], shift[4], q[4];     // cell of value x in band b: clamp((x - base) >> shift, 0, q - 1)
+    int tmin, tmax;                  // limits of the data type
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -45,6 +52,10 @@ struct ssg_ctx {
     DevBuf sortKeys0, sortKeys1, sortVals0, sortVals1;   // slow paths (oversized, ordered sums)
     DevBuf emuStack;
     DevBuf centres;   // double k*nBands
+    DevBuf assignGrid;                  // candidate-centre masks of the pruning grid (kept between calls)
+    std::vector<double> gridCentres;    // the centres it was built for
+    int gridDtype = -1, gridK = 0;
+    GridGeom gridGeom = {};
     std::vector<double> centresStage;
     std::vector<unsigned long long> grownStartStage;   // host copy of the merge kernel's list offsets
     DevBuf counters;  // small device counter block (see enum Counter)

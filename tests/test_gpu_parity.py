@@ -260,3 +260,57 @@ def test_result_properties_large(shepseg):
     assert seg.flat[0] >= 1
     want = oracle.doShepherdSegmentation(img, minSegmentSize=50, kmeansObj=km)
     same(seg, want.segimg, '4096x4096x4 vs oracle')
+
+
+ASSIGN_GRID_CASES = [
+    # (dtype, bands, k, how the centres are drawn)
+    (numpy.uint16, 4, 60, 'data'), (numpy.uint16, 3, 64, 'data'), (numpy.uint16, 2, 17, 'data'),
+    (numpy.uint16, 1, 9, 'data'), (numpy.uint8, 4, 33, 'data'), (numpy.int16, 3, 40, 'data'),
+    (numpy.uint16, 4, 60, 'integer'),        # integer centres: exact float64 ties, first minimum must win
+    (numpy.uint16, 4, 12, 'outside'),        # centres outside the data type's range
+    (numpy.int16, 4, 64, 'narrow'),          # all centres within a few units: one cell wide
+]
+
+
+@pytest.mark.parametrize('case', ASSIGN_GRID_CASES, ids=['%s_%db_k%d_%s' % (numpy.dtype(c[0]).name, c[1], c[2], c[3])
+    for c in ASSIGN_GRID_CASES])
+def test_assign_pruning_grid_equals_full_scan_and_oracle(shepseg, case):
+    """The pruned assignment (a few candidate centres per box of band space, assign.cu) must give
+    the float64 first-minimum argmin over ALL centres: compared with the oracle and with the
+    full scan of the same library (SSG_ASSIGN_GRID=0), on values that sit on box boundaries, on
+    the limits of the data type and on exact ties (shepseg.py:317-361)."""
+    (dtype, nB, k, how) = case
+    rng = numpy.random.default_rng(nB * 1000 + k)
+    info = numpy.iinfo(dtype)
+    (rows, cols) = (256, 512)
+    lo = int(info.min + (info.max - info.min) * 0.05)
+    hi = int(info.min + (info.max - info.min) * 0.4)
+    img = rng.integers(lo, hi, (nB, rows, cols)).astype(dtype)
+    img[:, :8, :] = rng.integers(info.min, info.max, (nB, 8, cols), endpoint=True).astype(dtype)   # anywhere
+    img[:, 8, :64] = info.min
+    img[:, 8, 64:128] = info.max
+    if how == 'data':
+        centres = rng.uniform(lo, hi, (k, nB))
+    elif how == 'integer':
+        centres = rng.integers(lo, hi, (k, nB)).astype(numpy.float64)
+        centres[1] = centres[0]             # two identical centres: the first must win everywhere
+        img[:, 9, :k] = ((centres[:k] + centres[(numpy.arange(k) + 1) % k]) // 2).T.astype(dtype)   # midpoints
+    elif how == 'outside':
+        centres = rng.uniform(-2.0 * info.max, 3.0 * info.max, (k, nB))
+    else:
+        centres = lo + rng.uniform(0.0, 3.0, (k, nB))
+    # values on the boundaries of the grid boxes (powers of two around the centre range)
+    for s in range(4, 14):
+        img[:, 10 + (s - 4), :] = numpy.clip(numpy.floor(centres.min()) + rng.integers(-2, 3, (nB, cols)) +
+            (rng.integers(-3, 40, (nB, cols)) << s), info.min, info.max).astype(dtype)
+    km = goldenutil.Centres(centres)
+    for nullVal in (None, int(img[0, 40, 40])):
+        want = oracle.applySpectralClusters(km, img, nullVal)
+        got = shepseg.applySpectralClusters(km, img, nullVal)
+        same(got, want, 'pruned assignment vs oracle (null %s)' % nullVal)
+        os.environ['SSG_ASSIGN_GRID'] = '0'
+        try:
+            full = shepseg.applySpectralClusters(km, img, nullVal)
+        finally:
+            del os.environ['SSG_ASSIGN_GRID']
+        same(got, full, 'pruned assignment vs full scan (null %s)' % nullVal)
