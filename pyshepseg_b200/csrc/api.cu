@@ -316,11 +316,13 @@ int ssg_eliminate_single_pixels(ssg_ctx *ctx, const void *img, int dtype, int nB
     SSG_CUDA(ctx, cudaMemcpyAsync(ctx->segSize.p, segSize, (size_t)len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     int64_t moved = 0;
     uint32_t rounds = 0, alive = 0;
+    const uint32_t *moveTo = nullptr;
     SSG_TRY(ssgk_eliminate_single(ctx, ctx->img.p, dtype, nBands, nRows, nCols, bufp<uint32_t>(ctx->seg),
-                                  bufp<uint32_t>(ctx->segSize), len, fourConnected, &moved, &rounds));
+                                  bufp<uint32_t>(ctx->segSize), len, fourConnected, &moved, &rounds, &moveTo));
     // the reference leaves segSize as mergeSinglePixels updated it and relabels seg (shepseg.py:615)
     SSG_CUDA(ctx, cudaMemcpyAsync(segSize, ctx->segSize.p, (size_t)len * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SSG_TRY(ssgk_relabel(ctx, bufp<uint32_t>(ctx->seg), N, bufp<uint32_t>(ctx->segSize), len, minSegId, &alive));
+    SSG_TRY(ssgk_relabel(ctx, bufp<uint32_t>(ctx->seg), N, bufp<uint32_t>(ctx->segSize), len, minSegId, &alive,
+                         nullptr, nullptr, moveTo));
     SSG_CUDA(ctx, cudaMemcpyAsync(seg, ctx->seg.p, (size_t)N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (numMoved) *numMoved = moved;
@@ -401,8 +403,9 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
 
     int64_t moved = 0;
     uint32_t rounds = 0;
+    const uint32_t *moveTo = nullptr;
     SSG_TRY(ssgk_eliminate_single(ctx, imgDev, prm->dtype, prm->nBands, prm->nRows, prm->nCols, segDev,
-                                  segSize, len, prm->fourConnected, &moved, &rounds,
+                                  segSize, len, prm->fourConnected, &moved, &rounds, &moveTo,
                                   numSingles >= 0 ? bufp<unsigned>(ctx->singles) : nullptr, numSingles));
     // the reference relabels here (eliminateSinglePixels ends with relabelSegments,
     // shepseg.py:615), and so do we: three quarters of the clump ids are gone, and every table
@@ -414,7 +417,7 @@ static int segment_tile_impl(ssg_ctx *ctx, const void *imgDev, const ssg_tile_pa
         SSG_TRY(ssg_reserve(ctx, ctx->aux2, (size_t)len * sizeof(unsigned)));
         unsigned *compact = bufp<unsigned>(ctx->aux2);
         // (worked out here, applied by the pixel pass of the next stage)
-        SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &afterSingles, compact, &pendingLut));
+        SSG_TRY(ssgk_relabel(ctx, segDev, N, segSize, len, 1, &afterSingles, compact, &pendingLut, moveTo));
         segSize = compact;
     }
     const int64_t len1 = (int64_t)afterSingles + 1;

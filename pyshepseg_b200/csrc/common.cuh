@@ -349,10 +349,11 @@ int ssgk_clump(ssg_ctx *ctx, const int32_t *clusterDev, int64_t nRows, int64_t n
                uint32_t *numClumps, uint32_t *numOversized, int64_t *singlesOut = nullptr);
 int ssgk_seg_size(ssg_ctx *ctx, const uint32_t *segDev, int64_t N, uint32_t *sizeDev, int64_t len);
 // cand0 / nCand0: the pixels of all single-pixel segments if the caller has them (device list),
-// else nullptr / -1 and the first round scans the raster
+// else nullptr / -1 and the first round scans the raster.  The label raster is not modified:
+// *moveToOut (nullptr if nothing moved) goes to ssgk_relabel, which ends the stage.
 int ssgk_eliminate_single(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
-                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, int64_t len,
-                          int four, int64_t *numMoved, uint32_t *numRounds,
+                          int64_t nCols, const uint32_t *segDev, uint32_t *sizeDev, int64_t len,
+                          int four, int64_t *numMoved, uint32_t *numRounds, const uint32_t **moveToOut,
                           const unsigned *cand0 = nullptr, int64_t nCand0 = -1);
 int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, uint32_t maxSegId,
@@ -360,7 +361,7 @@ int ssgk_eliminate_small(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands
                          uint32_t *numPasses, const uint32_t *pendingLut = nullptr, int64_t lutLen = 0);
 // sizeOutDev (optional, len entries, must not alias sizeDev): the sizes under the new numbering.
 // lutOut (optional): the relabel is only worked out, *lutOut (len entries, scratch of this call)
-// maps old to new ids and the caller applies it.
+// maps old to new ids and the caller applies it.  moveTo (optional): see ssgk_eliminate_single.
 int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
                  uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev = nullptr,
-                 const uint32_t **lutOut = nullptr);
+                 const uint32_t **lutOut = nullptr, const uint32_t *moveTo = nullptr);

@@ -39,10 +39,16 @@ namespace cg = cooperative_groups;
 // minimum of the int64 squared distance, only neighbours whose segment has more than one pixel.
 // The loads go out level by level (labels, sizes, then one band of all neighbours at a time) so
 // that their latencies overlap.
+// The label raster itself is not touched while single pixels move (scattered 4-byte stores into a
+// raster of tens of megabytes are what this GPU does worst: each is a read-modify-write of a DRAM
+// sector): a moved pixel's OLD id has size 0 and moveTo[old id] names the segment it joined, and
+// whoever looks at such a pixel follows that link (stored + 1; 0 = not moved).  The raster catches up in the relabel that
+// ends the stage (shepseg.py:615), which rewrites every label anyway.
 template <typename T, bool FOUR>
 __device__ bool nearest_neighbour(const T *__restrict__ img, int nB, int64_t nRows, int64_t nCols,
                                   const unsigned *__restrict__ seg,
-                                  const unsigned *__restrict__ segSize, int64_t p,
+                                  const unsigned *__restrict__ segSize,
+                                  const unsigned *__restrict__ moveTo, int64_t p,
                                   unsigned *newSeg)
 {
     const int64_t N = nRows * nCols;
@@ -61,6 +67,13 @@ __device__ bool nearest_neighbour(const T *__restrict__ img, int nB, int64_t nRo
     }
 #pragma unroll
     for (int q = 0; q < 8; q++) sz[q] = ok[q] ? segSize[sn[q]] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (ok[q] && sz[q] == 0) {          // a single pixel that moved in an earlier round
+            sn[q] = moveTo[sn[q]] - 1u;       // (stored + 1: segment 0, the null segment, is a possible target)
+            sz[q] = segSize[sn[q]];
+        }
+    }
     bool any = false;
 #pragma unroll
     for (int q = 0; q < 8; q++) { ok[q] = ok[q] && sz[q] > 1; any |= ok[q]; }
@@ -95,35 +108,37 @@ template <typename T, bool FOUR>
 __global__ void __launch_bounds__(256)
 k_single_decide(const T *__restrict__ img, int nB, int64_t nRows, int64_t nCols,
                 const unsigned *__restrict__ seg, const unsigned *__restrict__ segSize,
-                const unsigned *__restrict__ candIn, int64_t nIn, unsigned *movePix,
+                const unsigned *__restrict__ moveTo,
+                const unsigned *__restrict__ candIn, int64_t nIn, unsigned *moveOld,
                 unsigned *moveSeg, unsigned *candOut, unsigned long long *counters)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool cand = false;
     int64_t p = 0;
+    unsigned own = 0;
     if (t < nIn) {
         p = candIn ? (int64_t)candIn[t] : t;
-        cand = segSize[seg[p]] == 1;
+        own = seg[p];
+        cand = segSize[own] == 1;      // (a pixel that has moved has size 0 under its old id)
     }
     unsigned newSeg = 0;
     bool found = false;
-    if (cand) found = nearest_neighbour<T, FOUR>(img, nB, nRows, nCols, seg, segSize, p, &newSeg);
+    if (cand) found = nearest_neighbour<T, FOUR>(img, nB, nRows, nCols, seg, segSize, moveTo, p, &newSeg);
     unsigned long long s0 = warp_claim(&counters[C_NUM_MOVES], cand && found);
-    if (cand && found) { movePix[s0] = (unsigned)p; moveSeg[s0] = newSeg; }
+    if (cand && found) { moveOld[s0] = own; moveSeg[s0] = newSeg; }
     unsigned long long s1 = warp_claim(&counters[C_NUM_LEFT], cand && !found);
     if (cand && !found) candOut[s1] = (unsigned)p;
 }
 
-// apply phase (shepseg.py:664-672)
+// apply phase (shepseg.py:664-672), on the per-segment tables only
 __global__ void __launch_bounds__(256)
-k_single_apply(const unsigned *__restrict__ movePix, const unsigned *__restrict__ moveSeg,
-               int64_t n, unsigned *seg, unsigned *segSize)
+k_single_apply(const unsigned *__restrict__ moveOld, const unsigned *__restrict__ moveSeg,
+               int64_t n, unsigned *moveTo, unsigned *segSize)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const unsigned p = movePix[t], ns = moveSeg[t];
-    const unsigned old = seg[p];
-    seg[p] = ns;
+    const unsigned old = moveOld[t], ns = moveSeg[t];
+    moveTo[old] = ns + 1u;
     segSize[old] = 0;
     atomicAdd(&segSize[ns], 1u);
 }
@@ -140,14 +155,15 @@ k_count_size_eq(const unsigned *__restrict__ segSize, int64_t lo, int64_t len, u
 
 template <typename T>
 static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, int64_t nCols,
-                              unsigned *seg, unsigned *segSize, int64_t len, int four,
+                              const unsigned *seg, unsigned *segSize, int64_t len, int four,
                               int64_t *numMoved, unsigned *numRounds, const unsigned *cand0,
-                              int64_t nCand0)
+                              int64_t nCand0, const unsigned **moveToOut)
 {
     const int64_t N = nRows * nCols;
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
     *numMoved = 0;
     *numRounds = 0;
+    *moveToOut = nullptr;
     if (N == 0) return SSG_OK;
     // how many single-pixel segments are there (the lone null pixel counts, shepseg.py:652)
     int64_t nSingles = nCand0;
@@ -165,8 +181,11 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
     SSG_TRY(ssg_reserve(ctx, ctx->aux0, cap));
     SSG_TRY(ssg_reserve(ctx, ctx->aux1, cap));
     SSG_TRY(ssg_reserve(ctx, ctx->aux2, 2 * cap));
-    unsigned *movePix = bufp<unsigned>(ctx->aux0), *moveSeg = bufp<unsigned>(ctx->aux1);
+    SSG_TRY(ssg_reserve(ctx, ctx->mergeTo, (size_t)len * sizeof(unsigned)));
+    unsigned *moveOld = bufp<unsigned>(ctx->aux0), *moveSeg = bufp<unsigned>(ctx->aux1);
     unsigned *candA = bufp<unsigned>(ctx->aux2), *candB = candA + nSingles;
+    unsigned *moveTo = bufp<unsigned>(ctx->mergeTo);
+    SSG_CUDA(ctx, cudaMemsetAsync(moveTo, 0, (size_t)len * sizeof(unsigned), ctx->stream));
 
     const unsigned *candIn = cand0;
     int64_t nIn = cand0 ? nSingles : N;
@@ -175,11 +194,11 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
         SSG_CUDA(ctx, cudaMemsetAsync(counters + C_NUM_MOVES, 0, 2 * sizeof(unsigned long long), ctx->stream));
         SSG_PROF_BEGIN(ctx, "k_single_decide");
         if (four)
-            k_single_decide<T, true><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize,
-                                                                                 candIn, nIn, movePix, moveSeg, candOut, counters);
+            k_single_decide<T, true><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize, moveTo,
+                                                                                 candIn, nIn, moveOld, moveSeg, candOut, counters);
         else
-            k_single_decide<T, false><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize,
-                                                                                  candIn, nIn, movePix, moveSeg, candOut, counters);
+            k_single_decide<T, false><<<gridFor(nIn, 256), 256, 0, ctx->stream>>>(img, nB, nRows, nCols, seg, segSize, moveTo,
+                                                                                  candIn, nIn, moveOld, moveSeg, candOut, counters);
         SSG_LAUNCHED(ctx);
         SSG_TRY(ssg_fetch_counters(ctx));
         const int64_t nMoves = (int64_t)ctx->hostCounters[C_NUM_MOVES];
@@ -187,7 +206,7 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
         (*numRounds)++;
         if (nMoves == 0) break;   // the reference's last, empty round (shepseg.py:610)
         SSG_PROF_BEGIN(ctx, "k_single_apply");
-        k_single_apply<<<gridFor(nMoves, 256), 256, 0, ctx->stream>>>(movePix, moveSeg, nMoves, seg, segSize);
+        k_single_apply<<<gridFor(nMoves, 256), 256, 0, ctx->stream>>>(moveOld, moveSeg, nMoves, moveTo, segSize);
         SSG_LAUNCHED(ctx);
         *numMoved += nMoves;
         if (nLeft == 0) { (*numRounds)++; break; }   // nothing left to examine: the empty round is implied
@@ -195,18 +214,21 @@ static int eliminate_single_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows,
         nIn = nLeft;
         candOut = (candOut == candA) ? candB : candA;
     }
+    if (*numMoved > 0) *moveToOut = moveTo;
     return SSG_OK;
 }
 
+// seg is NOT modified: *moveToOut (len entries, scratch of this call; nullptr if nothing moved) maps
+// the old id of every moved pixel to the segment it joined and must be handed to ssgk_relabel
 int ssgk_eliminate_single(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t nRows,
-                          int64_t nCols, uint32_t *segDev, uint32_t *sizeDev, int64_t len,
-                          int four, int64_t *numMoved, uint32_t *numRounds, const unsigned *cand0,
-                          int64_t nCand0)
+                          int64_t nCols, const uint32_t *segDev, uint32_t *sizeDev, int64_t len,
+                          int four, int64_t *numMoved, uint32_t *numRounds, const uint32_t **moveToOut,
+                          const unsigned *cand0, int64_t nCand0)
 {
     switch (dtype) {
-    case SSG_U8: return eliminate_single_t<uint8_t>(ctx, (const uint8_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0);
-    case SSG_U16: return eliminate_single_t<uint16_t>(ctx, (const uint16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0);
-    case SSG_I16: return eliminate_single_t<int16_t>(ctx, (const int16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0);
+    case SSG_U8: return eliminate_single_t<uint8_t>(ctx, (const uint8_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0, moveToOut);
+    case SSG_U16: return eliminate_single_t<uint16_t>(ctx, (const uint16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0, moveToOut);
+    case SSG_I16: return eliminate_single_t<int16_t>(ctx, (const int16_t *)imgDev, nBands, nRows, nCols, segDev, sizeDev, len, four, numMoved, numRounds, cand0, nCand0, moveToOut);
     default: SSG_FAIL(ctx, SSG_ERR_ARG, "unsupported dtype code %d", dtype);
     }
 }
@@ -258,11 +280,23 @@ k_compact_sizes(const unsigned *__restrict__ segSize, const unsigned *__restrict
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= len) return;
     const unsigned z = segSize[s];
-    if (s < minSegId || z != 0) sizeOut[lut[s]] = z;
+    if (s < minSegId) sizeOut[s] = z;          // ids below minSegId keep their place (a null id whose one pixel moved: 0)
+    else if (z != 0) sizeOut[lut[s]] = z;
+}
+
+// ids whose pixels have moved elsewhere take the new id of the segment they joined
+__global__ void __launch_bounds__(256)
+k_redirect_lut(const unsigned *__restrict__ segSize, const unsigned *__restrict__ moveTo, int64_t len, unsigned *lut)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= len) return;
+    const unsigned to = moveTo[s];
+    if (to != 0 && segSize[s] == 0) lut[s] = lut[to - 1u];     // (the target is alive: its entry is final)
 }
 
 int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *sizeDev, int64_t len,
-                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev, const uint32_t **lutOut)
+                 uint32_t minSegId, uint32_t *numAlive, uint32_t *sizeOutDev, const uint32_t **lutOut,
+                 const uint32_t *moveTo)
 {
     if (lutOut) *lutOut = nullptr;
     unsigned long long *counters = bufp<unsigned long long>(ctx->counters);
@@ -283,6 +317,11 @@ int ssgk_relabel(ssg_ctx *ctx, uint32_t *segDev, int64_t N, const uint32_t *size
     SSG_PROF_BEGIN(ctx, "k_make_lut");
     k_make_lut<<<gridFor(len, 256), 256, 0, ctx->stream>>>(flag, sizeDev, len, minSegId, lut, counters);
     SSG_LAUNCHED(ctx);
+    if (moveTo) {
+        SSG_PROF_BEGIN(ctx, "k_redirect_lut");
+        k_redirect_lut<<<gridFor(len, 256), 256, 0, ctx->stream>>>(sizeDev, moveTo, len, lut);
+        SSG_LAUNCHED(ctx);
+    }
     if (lutOut) *lutOut = lut;        // the caller applies it (in a pass it makes over the labels anyway)
     else if (N > 0) {
         SSG_PROF_BEGIN(ctx, "k_apply_lut");

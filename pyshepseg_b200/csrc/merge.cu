@@ -447,13 +447,16 @@ k_rec_init(const float *__restrict__ fsum, const unsigned *__restrict__ segSize,
     constexpr int W = MergeRecWords<NBMAX>::value;
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= len) return;
-    unsigned *r = rec + (size_t)s * W;
+    unsigned r[W];
 #pragma unroll
     for (int b = 0; b < NBMAX; b++) r[b] = b < nB ? __float_as_uint(fsum[(size_t)s * nB + b]) : 0u;
     r[NBMAX] = segSize[s];
     r[NBMAX + 1] = sliceOff[s];
 #pragma unroll
     for (int b = NBMAX + 2; b < W; b++) r[b] = 0u;
+    uint4 *o = reinterpret_cast<uint4 *>(rec + (size_t)s * W);      // whole sectors, not words
+#pragma unroll
+    for (int i = 0; i < W / 4; i++) o[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
 template <int NBMAX, bool FOUR>

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/tile_launches_$TAG.csv $CMD > gpurun_out/tile_ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on \
-    -k regex:"^k_" -s 24 -c 26 \
+    -k regex:"^k_" -s 29 -c 28 \
     -o gpurun_out/tile_full_$TAG -f $CMD > gpurun_out/tile_ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
 ncu -i gpurun_out/tile_full_$TAG.ncu-rep --page raw --csv > gpurun_out/tile_full_raw_$TAG.csv 2>/dev/null
