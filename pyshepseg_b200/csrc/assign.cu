@@ -478,7 +478,14 @@ int ssgk_assign(ssg_ctx *ctx, const void *imgDev, int dtype, int nBands, int64_t
                     if (c < lo) lo = c;
                     if (c > hi) hi = c;
                 }
-                // (centres outside the data type's range cannot make the grid wider than the data)
+                // The fine boxes should cover the DATA, which reaches beyond the outermost centres by
+                // about a cluster radius: the range of the centres widened by 40 % on either side
+                // (pixels beyond that land in the two outer boxes, which reach to the limits of the
+                // data type and list many centres: correct, just slower).  Centres outside the data
+                // type's range cannot make the grid wider than the data.
+                const double widen = 0.4 * (hi - lo);
+                lo -= widen;
+                hi += widen;
                 long long cmin = (long long)floor(lo < tmin ? (double)tmin : (lo > tmax ? (double)tmax : lo));
                 long long cmax = (long long)ceil(hi > tmax ? (double)tmax : (hi < tmin ? (double)tmin : hi));
                 const int q = cellsPerBand[nBands];
