@@ -326,15 +326,11 @@ k_count_oversized(const unsigned *__restrict__ segSize, int64_t lo, int64_t len,
                   unsigned long long *counters)
 {
     const int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool over = s < len && segSize[s] > SSG_MAX_CLUMP_SIZE + 1;
-    bool single = s < len && segSize[s] == 1;
+    const bool over = s < len && segSize[s] > SSG_MAX_CLUMP_SIZE + 1;
+    const bool single = s < len && segSize[s] == 1;
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[C_NULL_SINGLE] = segSize[0] == 1 ? 1ull : 0ull;
-    unsigned mo = __ballot_sync(0xffffffffu, over);
-    unsigned ms = __ballot_sync(0xffffffffu, single);
-    if (lane_id() == 0) {
-        if (mo) atomicAdd(&counters[C_NUM_OVERSIZED], (unsigned long long)__popc(mo));
-        if (ms) atomicAdd(&counters[C_NUM_SINGLES], (unsigned long long)__popc(ms));
-    }
+    block_add(&counters[C_NUM_OVERSIZED], over ? 1u : 0u);
+    block_add(&counters[C_NUM_SINGLES], single ? 1u : 0u);
 }
 
 // labels (root pointers) -> dense ids in seg + size table; returns the number of roots

@@ -294,6 +294,21 @@ __device__ __forceinline__ unsigned long long warp_claim(unsigned long long *cou
     return base + __popc(m & ((1u << lane_id()) - 1u));
 }
 
+// A per-thread count added to a global counter with ONE atomic per block (every thread of the
+// block must call it): a counter that every warp of a large grid hits directly serialises
+// thousands of atomics on one address, which costs more than the kernels that do the counting.
+__device__ __forceinline__ void block_add(unsigned long long *counter, unsigned v)
+{
+    __shared__ unsigned long long blockAddSh;
+    if (threadIdx.x == 0) blockAddSh = 0ull;
+    __syncthreads();
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane_id() == 0 && v) atomicAdd(&blockAddSh, (unsigned long long)v);
+    __syncthreads();
+    if (threadIdx.x == 0 && blockAddSh) atomicAdd(counter, blockAddSh);
+    __syncthreads();
+}
+
 // Runs of equal keys over the lanes of a warp (consecutive pixels of a label raster are mostly
 // runs of a few segments).  A run never spans an invalid lane or a lane flagged `breakBefore`.
 // Cheaper than __match_any_sync + masked reductions: fixed cost, no divergence; a segment that

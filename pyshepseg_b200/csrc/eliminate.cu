@@ -148,9 +148,8 @@ k_count_size_eq(const unsigned *__restrict__ segSize, int64_t lo, int64_t len, u
                 unsigned long long *counter)
 {
     const int64_t s = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool hit = s < len && segSize[s] == value;
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (lane_id() == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
+    const bool hit = s < len && segSize[s] == value;
+    block_add(counter, hit ? 1u : 0u);
 }
 
 template <typename T>
@@ -254,8 +253,7 @@ k_make_lut(const unsigned *__restrict__ zerosBefore, const unsigned *__restrict_
         lut[s] = (unsigned)s - zerosBefore[s];
         alive = s >= minSegId && segSize[s] != 0;
     }
-    unsigned m = __ballot_sync(0xffffffffu, alive);
-    if (lane_id() == 0 && m) atomicAdd(&counters[C_NUM_ALIVE], (unsigned long long)__popc(m));
+    block_add(&counters[C_NUM_ALIVE], alive ? 1u : 0u);
 }
 
 __global__ void __launch_bounds__(256)
@@ -521,8 +519,7 @@ k_finalize_sums2(const unsigned long long *__restrict__ isum, const unsigned *__
         if (s == 0) big = false;
         bigFlag[s] = big ? 1 : 0;
     }
-    unsigned m = __ballot_sync(0xffffffffu, big);
-    if (lane_id() == 0 && m) atomicAdd(&counters[C_NUM_BIGSUM], (unsigned long long)__popc(m));
+    block_add(&counters[C_NUM_BIGSUM], big ? 1u : 0u);
 }
 
 // lutF[i] = (lut ? lut[i] : i) | small flag of the new id
@@ -561,12 +558,8 @@ k_small_census(const unsigned *__restrict__ segSize, int64_t len, unsigned minSe
     }
     if (s <= len) { cnt[s] = c; isSmall[s] = c ? 1u : 0u; }
     if (c) atomicAdd(&hist[c], 1u);
-    const unsigned m = __ballot_sync(0xffffffffu, c != 0);
-    const unsigned pixTot = __reduce_add_sync(0xffffffffu, c);
-    if (lane_id() == 0 && m) {
-        atomicAdd(&counters[C_NUM_SMALLSEG], (unsigned long long)__popc(m));
-        atomicAdd(&counters[C_NUM_SMALLPIX], (unsigned long long)pixTot);
-    }
+    block_add(&counters[C_NUM_SMALLSEG], c != 0 ? 1u : 0u);
+    block_add(&counters[C_NUM_SMALLPIX], c);
     __syncthreads();
     for (unsigned i = threadIdx.x; i < minSegSize; i += blockDim.x)
         if (hist[i]) atomicAdd(&sizeHist[i], hist[i]);
@@ -1388,10 +1381,10 @@ static int eliminate_small_t(ssg_ctx *ctx, const T *img, int nB, int64_t nRows, 
         ms.bucketStart = bucketStart; ms.bucketList = bucketList;
         ms.grownList = bufp<unsigned>(ctx->targetList); ms.grownStart = grownStart; ms.grownCount = grownCount;
         ms.ctr = mctr;
-        ms.bar = reinterpret_cast<SmallBarrier *>(mctr + 16);
+        ms.bar = nullptr;       // (set by the merge stage, which knows the layout of its counters)
         ms.dbg = getenv("SSG_SMALL_DEBUG") ? dbg : nullptr;
         if (ms.dbg) SSG_CUDA(ctx, cudaMemsetAsync(dbg, 0, 256 * sizeof(unsigned long long), ctx->stream));
-        ms.switchCands = 0; ms.switchMinT = 2;
+        ms.stage = 0; ms.exitSlots = 0; ms.switchMinT = 2;
         ms.nB = nB; ms.nRows = (unsigned)nRows; ms.nCols = (unsigned)nCols; ms.four = four;
         ms.minSegSize = minSegSize; ms.thr = thr;
         MergePlan plan;

@@ -53,7 +53,7 @@ enum MergeCtr {
     MC_PASSES,
     MC_RESUME_T,      // the size the tail kernel starts at
     MC_STAMP,         // pass number at hand-over
-    MC_COUNT = 8      // a second block of MC_COUNT follows for the tail kernel's parity sets
+    MC_COUNT = 8      // one block of MC_COUNT per launch of the chain (parity sets; the MC_* of the first count)
 };
 
 __device__ __forceinline__ float rec_mean(float sum, unsigned n)
@@ -104,20 +104,28 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
 
 // Barrier over the whole launch: the grid (cooperative launch: every block is resident) or the one
 // cluster.  On the way out every block picks up the find counters of parity `set`.
+// tallySh: what the warps of this block counted in the phase that ends here (candidates merged /
+// left, merges done): one global atomic per block and counter instead of one per warp -- a
+// thousand atomics on one address take microseconds, and the barrier waits for them
 template <bool CLUSTER>
 __device__ __forceinline__ void merge_barrier(const MergeState &st, unsigned long long *ctr, unsigned &phase, int set,
-                                              unsigned long long *curSh)
+                                              unsigned long long *curSh, unsigned *tallySh)
 {
-    if (st.safe & 4u) __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) {
+        if (tallySh[0]) atomicAdd(&ctr[set * MF_COUNT + MF_MERGED], (unsigned long long)tallySh[0]);
+        if (tallySh[1]) atomicAdd(&ctr[set * MF_COUNT + MF_LEFT], (unsigned long long)tallySh[1]);
+        if (tallySh[2]) atomicAdd(&st.ctr[MC_ELIM], (unsigned long long)tallySh[2]);
+        tallySh[0] = tallySh[1] = tallySh[2] = 0;
+    }
     if (CLUSTER) {
         if (threadIdx.x == 0) __threadfence();
         cg::this_cluster().sync();
     } else if (threadIdx.x == 0) {
         const unsigned target = (phase + 1) * gridDim.x;
         __threadfence();
-        atomicAdd(&st.bar->arrive, 1u);
-        while (ld_acquire_gpu(&st.bar->arrive) < target) { }
+        atomicAdd(&st.bar[st.stage].arrive, 1u);
+        while (ld_acquire_gpu(&st.bar[st.stage].arrive) < target) { }
     }
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -129,9 +137,9 @@ __device__ __forceinline__ void merge_barrier(const MergeState &st, unsigned lon
 
 // ---- find ---------------------------------------------------------------------------------------
 template <int NBMAX, bool FOUR>
-__device__ __forceinline__ void merge_find(const MergeState &st, unsigned long long *ctr, unsigned t,
+__device__ __forceinline__ void merge_find(const MergeState &st, unsigned *tallySh, unsigned t,
                                            const unsigned *listA, unsigned nA, const unsigned *listB, unsigned nCand,
-                                           unsigned stamp, int set, unsigned gtid, unsigned gsize)
+                                           unsigned stamp, unsigned gtid, unsigned gsize)
 {
     const unsigned G = width_for(t);
     const unsigned lane = lane_id();
@@ -151,10 +159,6 @@ __device__ __forceinline__ void merge_find(const MergeState &st, unsigned long l
         me.size = 0; me.off = 0;
         if (active) me = load_rec<NBMAX>(st.rec, s);
         active = active && me.size == t;          // merged (size 0) or grown since it was listed
-        if ((st.safe & 8u) && st.dbg && active && sub == 0) {
-            const unsigned long long was = atomicExch(&st.pendHead[s], ((unsigned long long)stamp << 32) | 0xffffffffull);
-            if ((unsigned)(was >> 32) == stamp) atomicAdd(&st.dbg[254], 1ull);     // seen twice (or a target!) this pass
-        }
         unsigned long long bestKey = ~0ull;
         unsigned bestU = 0;
         if (active) {
@@ -175,7 +179,7 @@ __device__ __forceinline__ void merge_find(const MergeState &st, unsigned long l
                     const int dy = cell / 3 - 1, dx = cell % 3 - 1;
                     const unsigned yy = y + (unsigned)dy, xx = x + (unsigned)dx;   // wraps below zero
                     ok[q] = yy < nRows && xx < nCols;
-                    nu[q] = ok[q] ? ((st.safe & 1u) ? __ldcg(st.seg + (size_t)yy * nCols + xx) : st.seg[(size_t)yy * nCols + xx]) : 0u;
+                    nu[q] = ok[q] ? st.seg[(size_t)yy * nCols + xx] : 0u;
                 }
 #pragma unroll
                 for (int q = 0; q < NQ; q++) {
@@ -241,16 +245,14 @@ __device__ __forceinline__ void merge_find(const MergeState &st, unsigned long l
     tallyMerged = __reduce_add_sync(0xffffffffu, tallyMerged);
     tallyLeft = __reduce_add_sync(0xffffffffu, tallyLeft);
     if (lane == 0) {
-        unsigned long long r0 = 0, r1 = 0;
-        if (tallyMerged) r0 = atomicAdd(&ctr[set * MF_COUNT + MF_MERGED], (unsigned long long)tallyMerged);
-        if (tallyLeft) r1 = atomicAdd(&ctr[set * MF_COUNT + MF_LEFT], (unsigned long long)tallyLeft);
-        if (st.safe & 2u) asm volatile("" :: "l"(r0), "l"(r1));    // wait for the atomics themselves
+        if (tallyMerged) atomicAdd(&tallySh[0], tallyMerged);
+        if (tallyLeft) atomicAdd(&tallySh[1], tallyLeft);
     }
 }
 
 // ---- merge --------------------------------------------------------------------------------------
 template <int NBMAX>
-__device__ __forceinline__ void merge_apply(const MergeState &st, unsigned long long *ctrGlobal, unsigned t,
+__device__ __forceinline__ void merge_apply(const MergeState &st, unsigned *tallySh, unsigned t,
                                             const unsigned *listA, unsigned nA, const unsigned *listB, unsigned nCand,
                                             unsigned stamp, unsigned gtid, unsigned gsize)
 {
@@ -368,7 +370,7 @@ __device__ __forceinline__ void merge_apply(const MergeState &st, unsigned long 
         }
     }
     elim = __reduce_add_sync(0xffffffffu, elim);
-    if (lane == 0 && elim) atomicAdd(&ctrGlobal[MC_ELIM], (unsigned long long)elim);
+    if (lane == 0 && elim) atomicAdd(&tallySh[2], elim);
 }
 
 // ---- the loop over sizes --------------------------------------------------------------------------
@@ -377,19 +379,22 @@ __global__ void __launch_bounds__(MERGE_THREADS, MINB)
 k_merge(MergeState st)
 {
     __shared__ unsigned long long cur[MF_COUNT];
+    __shared__ unsigned tally[4];
+    if (threadIdx.x < 4) tally[threadIdx.x] = 0;
+    __syncthreads();
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned gsize = gridDim.x * blockDim.x;
     unsigned long long *ctrG = st.ctr;                                // MC_* live in the first block
-    unsigned long long *ctr = st.ctr + (CLUSTER ? MC_COUNT : 0);      // parity sets of this kernel
+    unsigned long long *ctr = st.ctr + st.stage * MC_COUNT;           // parity sets of this launch
     unsigned phase = 0;
     unsigned long long base[2][MF_COUNT] = {{0, 0}, {0, 0}};
     unsigned long long passes = 0;
     unsigned stamp = 0;
     unsigned tBegin = 1;
-    if (CLUSTER) {
+    if (st.stage > 0) {
         tBegin = (unsigned)__ldcg(&ctrG[MC_RESUME_T]);
         stamp = (unsigned)__ldcg(&ctrG[MC_STAMP]);
-        if (tBegin == 0 || tBegin >= (unsigned)st.minSegSize) return;    // the grid kernel did it all
+        if (tBegin == 0 || tBegin >= (unsigned)st.minSegSize) return;    // an earlier launch did it all
     }
     const bool dbgOn = st.dbg != nullptr && gtid == 0;
     for (unsigned t = tBegin; t < (unsigned)st.minSegSize; t++) {
@@ -397,13 +402,13 @@ k_merge(MergeState st)
         const unsigned a0 = st.bucketStart[t];
         const unsigned nA = st.bucketStart[t + 1] - a0;
         const unsigned nCand = nA + __ldcg(&st.grownCount[t]);
-        if (!CLUSTER && st.switchCands != 0 && t >= st.switchMinT && nCand <= st.switchCands) {
-            // few candidates from here on: the cluster kernel takes over (every block takes this
-            // branch: the counts are the same for all of them)
+        if (st.exitSlots != 0 && t >= st.switchMinT && (unsigned long long)nCand * width_for(t) <= st.exitSlots) {
+            // few enough candidates for the next launch of the chain (fewer, leaner blocks; in the
+            // end one cluster).  Every block takes this branch: the counts are the same for all.
             if (gtid == 0) {
                 ctrG[MC_RESUME_T] = t;
                 ctrG[MC_STAMP] = stamp;
-                ctrG[MC_PASSES] = passes;
+                ctrG[MC_PASSES] = __ldcg(&ctrG[MC_PASSES]) + passes;
             }
             return;
         }
@@ -414,27 +419,27 @@ k_merge(MergeState st)
         for (int pass = 0; pass < 10; pass++) {              // shepseg.py:979-980
             const int set = (int)(phase & 1u);
             stamp++;
-            merge_find<NBMAX, FOUR>(st, ctr, t, listA, nA, listB, nCand, stamp, set, gtid, gsize);
-            merge_barrier<CLUSTER>(st, ctr, phase, set, cur);
+            merge_find<NBMAX, FOUR>(st, tally, t, listA, nA, listB, nCand, stamp, gtid, gsize);
+            merge_barrier<CLUSTER>(st, ctr, phase, set, cur, tally);
             const unsigned long long merged = cur[MF_MERGED] - base[set][MF_MERGED];
             const unsigned long long left = cur[MF_LEFT] - base[set][MF_LEFT];
 #pragma unroll
             for (int i = 0; i < MF_COUNT; i++) base[set][i] = cur[i];
             passes++;
             if (merged == 0) break;      // the count of this size did not change (shepseg.py:980,996)
-            merge_apply<NBMAX>(st, ctrG, t, listA, nA, listB, nCand, stamp, gtid, gsize);
-            merge_barrier<CLUSTER>(st, ctr, phase, set, cur);    // (the find counters did not move)
+            merge_apply<NBMAX>(st, tally, t, listA, nA, listB, nCand, stamp, gtid, gsize);
+            merge_barrier<CLUSTER>(st, ctr, phase, set, cur, tally);    // (the find counters did not move)
             done += merged;
             if (left == 0) break;        // nobody left of this size: the next pass would merge nothing
         }
         if (dbgOn && t < 90) {
             st.dbg[16 + 2 * t] = (unsigned long long)(clock64() - tStart);
-            st.dbg[16 + 2 * t + 1] = ((unsigned long long)(CLUSTER ? 1 : 0) << 63) | ((unsigned long long)nCand << 32) | done;
+            st.dbg[16 + 2 * t + 1] = ((unsigned long long)st.stage << 62) | ((unsigned long long)nCand << 32) | done;
         }
     }
     if (gtid == 0) {
-        ctrG[MC_PASSES] = (CLUSTER ? __ldcg(&ctrG[MC_PASSES]) : 0ull) + passes;
-        if (!CLUSTER) ctrG[MC_RESUME_T] = 0;
+        ctrG[MC_PASSES] = __ldcg(&ctrG[MC_PASSES]) + passes;
+        ctrG[MC_RESUME_T] = 0;
     }
 }
 
@@ -459,27 +464,39 @@ k_rec_init(const float *__restrict__ fsum, const unsigned *__restrict__ segSize,
     for (int i = 0; i < W / 4; i++) o[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
+#define MERGE_STAGES 3
+
 template <int NBMAX, bool FOUR>
 static int run_merge_t(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint32_t *numPasses, int64_t *numElim)
 {
-    const size_t ctrBytes = 2 * MC_COUNT * sizeof(unsigned long long) + sizeof(SmallBarrier);
+    const size_t ctrBytes = MERGE_STAGES * MC_COUNT * sizeof(unsigned long long) + MERGE_STAGES * sizeof(SmallBarrier);
+    st.bar = reinterpret_cast<SmallBarrier *>(st.ctr + MERGE_STAGES * MC_COUNT);
     SSG_CUDA(ctx, cudaMemsetAsync(st.ctr, 0, ctrBytes, ctx->stream));
     SSG_PROF_BEGIN(ctx, "k_rec_init");
     k_rec_init<NBMAX><<<gridFor(plan.len, 256), 256, 0, ctx->stream>>>(plan.fsum, st.segSize, plan.sliceOff, st.nB, plan.len, st.rec);
     SSG_LAUNCHED(ctx);
+    st.safe = 0;
+    if (const char *e = getenv("SSG_MERGE_SAFE")) st.safe = (unsigned)atoi(e);
+    st.switchMinT = 2;
 
-    // the tail kernel: one cluster of MERGE_CLUSTER blocks; without it the grid kernel does all sizes
-    bool tail = true;
+    // A chain of three launches, each picking up where the previous one stopped:
+    //   wide    two blocks per SM (64 registers): the first sizes, whose phases are hundreds of
+    //           thousands of gathers and want every warp the GPU can hold;
+    //   lean    one block per SM with all the registers it wants (no spills): the long run of sizes
+    //           whose phases are one dependent chain per candidate;
+    //   cluster one cluster of 16 blocks: the end, when a hardware cluster barrier beats a grid barrier.
+    bool lean = true, tail = true;
+    if (const char *e = getenv("SSG_MERGE_LEAN")) lean = atoi(e) != 0;
     if (const char *e = getenv("SSG_MERGE_TAIL")) tail = atoi(e) != 0;
     auto kTail = k_merge<NBMAX, FOUR, true, 1>;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
     if (tail) {
         if (cudaFuncSetAttribute(kTail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
             cudaGetLastError();
             tail = false;
         }
     }
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
     if (tail) {
         cfg.gridDim = dim3(MERGE_CLUSTER);
         cfg.blockDim = dim3(MERGE_THREADS);
@@ -494,34 +511,47 @@ static int run_merge_t(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint
             tail = false;
         }
     }
-    st.safe = 0;
-    if (const char *e = getenv("SSG_MERGE_SAFE")) st.safe = (unsigned)atoi(e);
-    st.switchCands = 0;
-    st.switchMinT = 2;
-    if (tail) {
-        st.switchCands = 320;       // measured (profiles/r2_merge.md): below this a 16-CTA cluster finishes a pass sooner than the grid
-        if (const char *e = getenv("SSG_MERGE_SWITCH")) st.switchCands = (unsigned)atoi(e);
-        if (const char *e = getenv("SSG_MERGE_SWITCH_T")) st.switchMinT = (unsigned)atoi(e);
-        if (st.switchCands == 0) tail = false;
-    }
+    unsigned tailCands = 320;      // measured (profiles/): below this a 16-CTA cluster finishes a pass sooner than the grid
+    if (const char *e = getenv("SSG_MERGE_SWITCH")) tailCands = (unsigned)atoi(e);
+    if (tailCands == 0) tail = false;
+    // the wide launch hands over when one sweep of the lean grid covers the candidates
+    unsigned long long leanSlots = (unsigned long long)ctx->numSMs * MERGE_THREADS;
+    if (const char *e = getenv("SSG_MERGE_LEAN_SLOTS")) leanSlots = (unsigned long long)atoll(e);
 
-    // two blocks per SM (64 registers, a few spills) hide more of the gather latency of the first
-    // sizes than one block with all the registers it wants
-    int want = 2;
-    if (const char *e = getenv("SSG_MERGE_BLOCKS_PER_SM")) want = atoi(e) >= 2 ? 2 : 1;
-    void *kGrid = want == 2 ? (void *)k_merge<NBMAX, FOUR, false, 2> : (void *)k_merge<NBMAX, FOUR, false, 1>;
+    void *kWide = (void *)k_merge<NBMAX, FOUR, false, 2>;
+    void *kLean = (void *)k_merge<NBMAX, FOUR, false, 1>;
+    int wantWide = 2;
+    if (const char *e = getenv("SSG_MERGE_BLOCKS_PER_SM")) wantWide = atoi(e) >= 2 ? 2 : 1;
+    if (wantWide == 1) { kWide = kLean; lean = false; }
     int perSM = 0;
-    SSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kGrid, MERGE_THREADS, 0));
+    SSG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kWide, MERGE_THREADS, 0));
     if (perSM < 1) SSG_FAIL(ctx, SSG_ERR_CUDA, "merge kernel does not fit on an SM");
-    if (perSM > want) perSM = want;
-    dim3 grid((unsigned)(ctx->numSMs * perSM)), block(MERGE_THREADS);
-    void *args[] = {&st};
-    SSG_PROF_BEGIN(ctx, "k_merge_grid");
-    SSG_CUDA(ctx, cudaLaunchCooperativeKernel(kGrid, grid, block, args, 0, ctx->stream));
-    SSG_LAUNCHED(ctx);
+    if (perSM > wantWide) perSM = wantWide;
+    dim3 block(MERGE_THREADS);
+    {
+        MergeState s0 = st;
+        s0.stage = 0;
+        s0.exitSlots = lean ? leanSlots : (tail ? (unsigned long long)tailCands * 32ull : 0ull);
+        void *args[] = {&s0};
+        SSG_PROF_BEGIN(ctx, "k_merge_wide");
+        SSG_CUDA(ctx, cudaLaunchCooperativeKernel(kWide, dim3((unsigned)(ctx->numSMs * perSM)), block, args, 0, ctx->stream));
+        SSG_LAUNCHED(ctx);
+    }
+    if (lean) {
+        MergeState s1 = st;
+        s1.stage = 1;
+        s1.exitSlots = tail ? (unsigned long long)tailCands * 32ull : 0ull;
+        void *args[] = {&s1};
+        SSG_PROF_BEGIN(ctx, "k_merge_lean");
+        SSG_CUDA(ctx, cudaLaunchCooperativeKernel(kLean, dim3((unsigned)ctx->numSMs), block, args, 0, ctx->stream));
+        SSG_LAUNCHED(ctx);
+    }
     if (tail) {
+        MergeState s2 = st;
+        s2.stage = 2;
+        s2.exitSlots = 0;
         SSG_PROF_BEGIN(ctx, "k_merge_tail");
-        SSG_CUDA(ctx, cudaLaunchKernelEx(&cfg, kTail, st));
+        SSG_CUDA(ctx, cudaLaunchKernelEx(&cfg, kTail, s2));
         SSG_LAUNCHED(ctx);
     }
     uint64_t *host = ctx->hostCounters;   // the pinned mirror doubles as the landing zone
@@ -532,24 +562,19 @@ static int run_merge_t(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint
     if (st.dbg && (st.safe & 8u)) {
         unsigned long long chk[6];
         SSG_CUDA(ctx, cudaMemcpy(chk, st.dbg + 250, sizeof(chk), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "  merge checks: not in chain %llu, pixel out of range %llu, pixel with foreign label %llu, target not larger %llu, candidate seen twice %llu\n",
-                chk[0], chk[1], chk[2], chk[3], chk[4]);
-        unsigned long long v[36];
-        SSG_CUDA(ctx, cudaMemcpy(v, st.dbg + 200, sizeof(v), cudaMemcpyDeviceToHost));
-        for (int n = 0; n < 6; n++)
-            if (v[6 * n])
-                fprintf(stderr, "    foreign: size %llu candidate %llu (%s) pixel %llu carries %llu, list position %llu, target %llu\n", v[6 * n],
-                        v[6 * n + 1], (v[6 * n + 5] >> 32) ? "grown" : "bucket", v[6 * n + 2], v[6 * n + 3], v[6 * n + 4], v[6 * n + 5] & 0xffffffffull);
+        fprintf(stderr, "  merge checks: not in chain %llu, pixel out of range %llu, pixel with foreign label %llu, target not larger %llu\n",
+                chk[0], chk[1], chk[2], chk[3]);
     }
     if (st.dbg) {
         unsigned long long pt[240];
         SSG_CUDA(ctx, cudaMemcpy(pt, st.dbg, sizeof(pt), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "  merge: %u blocks x %d, tail %s (switch at <= %u candidates), us per size (candidates/merged, * = cluster):",
-                grid.x, MERGE_THREADS, tail ? "on" : "off", st.switchCands);
+        fprintf(stderr, "  merge: wide %d blocks per SM until <= %llu lanes of candidates, lean %s, cluster %s (<= %u candidates); us per size "
+                "(candidates/merged, ' = lean, * = cluster):", perSM, leanSlots, lean ? "on" : "off", tail ? "on" : "off", tailCands);
         for (int t = 1; t < st.minSegSize && t < 90; t++) {
             const unsigned long long v = pt[16 + 2 * t + 1];
+            const int stage = (int)(v >> 62);
             fprintf(stderr, "%s %d:%.0f%s(%llu/%llu)", (t % 6 == 1) ? "\n   " : "", t, pt[16 + 2 * t] / 1965.0,
-                    (v >> 63) ? "*" : "", (v >> 32) & 0x7fffffffull, v & 0xffffffffull);
+                    stage == 2 ? "*" : (stage == 1 ? "'" : ""), (v >> 32) & 0x3fffffffull, v & 0xffffffffull);
         }
         fprintf(stderr, "\n");
     }
@@ -562,7 +587,7 @@ size_t ssgk_merge_rec_bytes(int nB, int64_t len)
     return (size_t)len * w * sizeof(unsigned);
 }
 
-size_t ssgk_merge_ctr_bytes(void) { return 2 * MC_COUNT * sizeof(unsigned long long) + sizeof(SmallBarrier) + 64; }
+size_t ssgk_merge_ctr_bytes(void) { return MERGE_STAGES * MC_COUNT * sizeof(unsigned long long) + MERGE_STAGES * sizeof(SmallBarrier) + 64; }
 
 int ssgk_merge_regions(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint32_t *numPasses, int64_t *numElim)
 {

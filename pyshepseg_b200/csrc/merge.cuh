@@ -26,10 +26,12 @@ struct MergeState {
     const unsigned long long *grownStart;   // minSegSize + 1 offsets into grownList
     unsigned *grownCount;              // minSegSize + 1, zeroed
     unsigned long long *ctr;           // counters (2 x MC_COUNT), then the SmallBarrier
-    SmallBarrier *bar;
+    SmallBarrier *bar;                 // one per launch of the chain
     unsigned long long *dbg;
     unsigned safe;                     // debugging switches (SSG_MERGE_SAFE)
-    unsigned switchCands, switchMinT;  // hand over to the cluster kernel at the first size >= switchMinT with <= switchCands candidates
+    unsigned stage;                    // which launch of the chain this is (0 wide grid, 1 lean grid, 2 cluster)
+    unsigned long long exitSlots;      // stop at the first size >= switchMinT whose candidates x lanes fit this (0: run to the end)
+    unsigned switchMinT;
     int nB;
     unsigned nRows, nCols;
     int four;
