@@ -14,7 +14,7 @@
 //
 // How it runs here.  A pass is two phases separated by a barrier, nothing else:
 //   find   a group of G lanes per candidate (G = the candidate's size rounded up to a power of two,
-//          at most 32): ONE 32-byte record {band sums, size, list offset} per segment means one
+//          at most 32): ONE 32-byte record {band MEANS, size, list offset} per segment means one
 //          gather tells everything about the candidate and one gather per neighbouring segment
 //          tells whether it is larger and how far away it is spectrally.  The winner is recorded as
 //          mergeTo[s] and s is pushed on the target's pending stack (one atomic exchange; the
@@ -162,12 +162,16 @@ __device__ __forceinline__ void merge_find(const MergeState &st, unsigned *tally
         unsigned long long bestKey = ~0ull;
         unsigned bestU = 0;
         if (active) {
-            float ms[NBMAX];
+            float ms[NBMAX];       // (the records hold the float32 MEANS: see k_rec_init)
 #pragma unroll
-            for (int b = 0; b < NBMAX; b++) ms[b] = b < nB ? rec_mean(me.f[b], t) : 0.0f;
+            for (int b = 0; b < NBMAX; b++) ms[b] = me.f[b];
             for (unsigned i = sub; i < t; i += G) {
                 const unsigned p = __ldcg(st.pix + me.off + i);
-                const unsigned y = p / nCols, x = p - y * nCols;
+                // row = p / nCols by multiplication (colMagic = floor(2^40 / nCols) + 1 overshoots by at
+                // most one for p < 2^32)
+                unsigned y = (unsigned)(((unsigned long long)p * st.colMagic) >> 40);
+                if (y * nCols > p) y--;
+                const unsigned x = p - y * nCols;
                 constexpr int NQ = FOUR ? 4 : 8;
                 unsigned nu[NQ];
                 bool ok[NQ];
@@ -204,8 +208,7 @@ __device__ __forceinline__ void merge_find(const MergeState &st, unsigned *tally
 #pragma unroll
                         for (int b = 0; b < NBMAX; b++) {
                             if (b < nB) {
-                                const float mu = rec_mean(nr[e].f[b], nr[e].size);
-                                const float df = __fsub_rn(ms[b], mu);
+                                const float df = __fsub_rn(ms[b], nr[e].f[b]);
                                 d = __fadd_rn(d, __fmul_rn(df, df));
                             }
                         }
@@ -335,6 +338,9 @@ __device__ __forceinline__ void merge_apply(const MergeState &st, unsigned *tall
         if (active && below == 0) {      // the group of the target's smallest source goes on
             const unsigned newSize = tg.size + k * t;              // every source has exactly t pixels
             const bool keepList = newSize < (unsigned)st.minSegSize;   // then the target was small all along
+            float fu[NBMAX];      // float32 band sums of the target (spectSum, shepseg.py:1117-1120)
+#pragma unroll
+            for (int b = 0; b < NBMAX; b++) fu[b] = b < nB ? __ldcg(st.fsum + (size_t)u * nB + b) : 0.0f;
             unsigned last = 0;   // ids are >= 1
             for (unsigned m = 0; m < k; m++) {
                 unsigned sm;
@@ -344,21 +350,25 @@ __device__ __forceinline__ void merge_apply(const MergeState &st, unsigned *tall
                     for (unsigned q = (unsigned)head; q != 0; q = __ldcg(st.pendNext + q))
                         if (q > last && q < sm) sm = q;
                 }
-                const Rec<NBMAX> sr = load_rec<NBMAX>(st.rec, sm);     // (sums and offset; its size word may be 0 already)
 #pragma unroll
                 for (int b = 0; b < NBMAX; b++)
-                    if (b < nB) tg.f[b] = __fadd_rn(tg.f[b], sr.f[b]);
+                    if (b < nB) fu[b] = __fadd_rn(fu[b], __ldcg(st.fsum + (size_t)sm * nB + b));
                 if (keepList) {
+                    const unsigned srcOff = __ldcg(st.rec + (size_t)sm * W + NBMAX + 1);
                     const unsigned dst = tg.off + tg.size + m * t;
-                    for (unsigned i = sub; i < t; i += G) st.pix[dst + i] = __ldcg(st.pix + sr.off + i);
+                    for (unsigned i = sub; i < t; i += G) st.pix[dst + i] = __ldcg(st.pix + srcOff + i);
                 }
                 last = sm;
             }
             if (sub == 0) {
                 unsigned *r = st.rec + (size_t)u * W;
 #pragma unroll
-                for (int b = 0; b < NBMAX; b++)
-                    if (b < nB) r[b] = __float_as_uint(tg.f[b]);
+                for (int b = 0; b < NBMAX; b++) {
+                    if (b < nB) {
+                        st.fsum[(size_t)u * nB + b] = fu[b];
+                        r[b] = __float_as_uint(rec_mean(fu[b], newSize));
+                    }
+                }
                 r[NBMAX] = newSize;
                 st.segSize[u] = newSize;
                 elim += k;
@@ -453,9 +463,11 @@ k_rec_init(const float *__restrict__ fsum, const unsigned *__restrict__ segSize,
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= len) return;
     unsigned r[W];
+    const unsigned size = segSize[s];
 #pragma unroll
-    for (int b = 0; b < NBMAX; b++) r[b] = b < nB ? __float_as_uint(fsum[(size_t)s * nB + b]) : 0u;
-    r[NBMAX] = segSize[s];
+    for (int b = 0; b < NBMAX; b++)
+        r[b] = (b < nB && size != 0) ? __float_as_uint(rec_mean(fsum[(size_t)s * nB + b], size)) : 0u;
+    r[NBMAX] = size;
     r[NBMAX + 1] = sliceOff[s];
 #pragma unroll
     for (int b = NBMAX + 2; b < W; b++) r[b] = 0u;
@@ -478,6 +490,8 @@ static int run_merge_t(ssg_ctx *ctx, MergeState &st, const MergePlan &plan, uint
     st.safe = 0;
     if (const char *e = getenv("SSG_MERGE_SAFE")) st.safe = (unsigned)atoi(e);
     st.switchMinT = 2;
+    st.fsum = const_cast<float *>(plan.fsum);
+    st.colMagic = ((1ull << 40) / st.nCols) + 1ull;
 
     // A chain of three launches, each picking up where the previous one stopped:
     //   wide    two blocks per SM (64 registers): the first sizes, whose phases are hundreds of

@@ -8,14 +8,16 @@ struct SmallBarrier {
     unsigned pad[31];
 };
 
-// words of one segment record {float sums[NBMAX]; uint size; uint listOffset; pad}: 32 / 64 / 128 bytes
+// words of one segment record {float means[NBMAX]; uint size; uint listOffset; pad}: 32 / 64 / 128 bytes
 template <int NBMAX>
 struct MergeRecWords { static constexpr int value = NBMAX <= 4 ? 8 : (NBMAX <= 8 ? 16 : 32); };
 
 struct MergeState {
     unsigned *seg;
     unsigned *segSize;                 // kept in step for the relabel that follows (0 = dead)
-    unsigned *rec;                     // len records
+    unsigned *rec;                     // len records {float32 band means, size, list offset}
+    float *fsum;                       // len x nB float32 band sums (touched by merges only)
+    unsigned long long colMagic;       // floor(2^40 / nCols) + 1: row of a pixel index without a division
     unsigned *pix;                     // per-segment list regions of regionCap entries
     unsigned *mergeTo;                 // len, zeroed
     unsigned long long *pendHead;      // len, zeroed: (pass stamp << 32) | last pushed source
