@@ -251,6 +251,17 @@ int ssg_memcpy2d_d2h(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, si
 int ssg_memcpy2d_h2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch,
                      size_t widthBytes, size_t rows);
 int ssg_memset_d(ssg_ctx *ctx, void *dst, int value, size_t bytes);
+/* the same device-to-host copies without waiting for them, and marks to wait on later: the tiled
+ * driver lets the last (largest) window travel while the host already works on the histogram
+ * (HistogramAccumulator / utils.estimateStatsFromHisto, tiling.py:1915-1963, utils.py:47-95).
+ * The host buffer should be pinned (ssg_host_alloc) or the copy is not asynchronous. */
+int ssg_memcpy_d2h_async(ssg_ctx *ctx, void *dst, const void *src, size_t bytes);
+int ssg_memcpy2d_d2h_async(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch,
+                           size_t widthBytes, size_t rows);
+/* record mark `slot` (0..2) on the context's stream / block the host until it has been reached */
+int ssg_mark(ssg_ctx *ctx, int slot);
+int ssg_wait_mark(ssg_ctx *ctx, int slot);
+
 
 /* per-kernel device timing: while enabled every kernel launch is bracketed by two CUDA
  * events on the context's stream; ssg_profile_fetch writes "name count total_ms" lines for

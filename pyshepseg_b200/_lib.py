@@ -104,6 +104,10 @@ SIGNATURES = {
     'ssg_memcpy2d_d2h': (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     'ssg_memcpy2d_h2d': (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     'ssg_memset_d': (_i, [_vp, _vp, _i, _sz]),
+    'ssg_memcpy_d2h_async': (_i, [_vp, _vp, _vp, _sz]),
+    'ssg_memcpy2d_d2h_async': (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
+    'ssg_mark': (_i, [_vp, _i]),
+    'ssg_wait_mark': (_i, [_vp, _i]),
     'ssg_launch_count': (_c.c_uint64, [_vp]),
     'ssg_profile_enable': (_i, [_vp, _i]),
     'ssg_profile_fetch': (_i, [_vp, _c.c_char_p, _sz]),

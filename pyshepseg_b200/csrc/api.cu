@@ -217,6 +217,32 @@ int ssg_memcpy2d_h2d(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, si
     SSG_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->stream));
     return SSG_OK;
 }
+int ssg_memcpy_d2h_async(ssg_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SSG_OK;
+}
+int ssg_memcpy2d_d2h_async(ssg_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t widthBytes, size_t rows)
+{
+    CTX_ENTER(ctx);
+    SSG_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, widthBytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    return SSG_OK;
+}
+int ssg_mark(ssg_ctx *ctx, int slot)
+{
+    CTX_ENTER(ctx);
+    if (slot < 0 || slot > 2) SSG_FAIL(ctx, SSG_ERR_ARG, "mark slot %d not in 0..2", slot);
+    SSG_CUDA(ctx, cudaEventRecord(ctx->ev[5 + slot], ctx->stream));
+    return SSG_OK;
+}
+int ssg_wait_mark(ssg_ctx *ctx, int slot)
+{
+    CTX_ENTER(ctx);
+    if (slot < 0 || slot > 2) SSG_FAIL(ctx, SSG_ERR_ARG, "mark slot %d not in 0..2", slot);
+    SSG_CUDA(ctx, cudaEventSynchronize(ctx->ev[5 + slot]));
+    return SSG_OK;
+}
 int ssg_memset_d(ssg_ctx *ctx, void *dst, int value, size_t bytes)
 {
     CTX_ENTER(ctx);

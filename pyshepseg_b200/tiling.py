@@ -739,8 +739,11 @@ class TiledSegmenter(object):
         from . import distributed
         return distributed.TileTable(tables.maxId, tables.countNew, rank, flags, pairKeys, pairCounts)
 
-    def applyLut(self, slot, tile, lut, maxId, sink, hist, histLen):
-        """Device phase 2: final ids over the trimmed window, on the device, then to the sink."""
+    def applyLut(self, slot, tile, lut, maxId, sink, hist, histLen, deferred=None, fetchLen=0):
+        """Device phase 2: final ids over the trimmed window, on the device, then to the sink.
+        deferred (a list, for the last tile of a run): if the window can travel on its own, the
+        histogram copy is queued BEFORE it (mark 0), the window copy is left in flight (mark 1)
+        and 'window' is appended to the list: the caller works on the histogram meanwhile."""
         ctx = slot.ctx
         (top, bottom, left, right) = tileMargins(self.tileInfo, tile.col, tile.row, tile.xsize,
             tile.ysize, self.overlapSize)
@@ -761,8 +764,16 @@ class TiledSegmenter(object):
             if (type(sink) is rasterfile.MemorySink and isinstance(arr, numpy.ndarray) and
                     arr.flags.c_contiguous and arr.dtype == numpy.uint32):
                 # the output raster is plain host memory: land the window in place
-                ctx.call('ssg_memcpy2d_d2h', arr.ctypes.data + (yout * arr.shape[1] + xout) * 4,
-                    arr.shape[1] * 4, winDev, wc * 4, wc * 4, wr)
+                if deferred is not None:
+                    hist.fetchAsync(ctx, fetchLen)
+                    ctx.call('ssg_mark', 0)
+                    ctx.call('ssg_memcpy2d_d2h_async', arr.ctypes.data + (yout * arr.shape[1] + xout) * 4,
+                        arr.shape[1] * 4, winDev, wc * 4, wc * 4, wr)
+                    ctx.call('ssg_mark', 1)
+                    deferred.append('window')
+                else:
+                    ctx.call('ssg_memcpy2d_d2h', arr.ctypes.data + (yout * arr.shape[1] + xout) * 4,
+                        arr.shape[1] * 4, winDev, wc * 4, wc * 4, wr)
             else:
                 out = window[:wr * wc].reshape(wr, wc)
                 ctx.call('ssg_memcpy_d2h', _lib.ptr(out), winDev, wr * wc * 4)
@@ -771,7 +782,7 @@ class TiledSegmenter(object):
             self.d2hBytes += wr * wc * 4
         self.h2dBytes += lut.nbytes
 
-    def stitchOne(self, slot, pool, tile, offset, sink, hist):
+    def stitchOne(self, slot, pool, tile, offset, sink, hist, deferred=None):
         self.mark('tile %d,%d stitch start' % (tile.col, tile.row))
         ov = self.overlapSize
         up = self.tiles.get((tile.col, tile.row - 1)) if tile.row > 0 else None
@@ -797,7 +808,8 @@ class TiledSegmenter(object):
         n = tb.maxId + 1
         self.mark('tile %d,%d resolved' % (tile.col, tile.row))
         self.applyLut(slot, tile, lut, tb.maxId, sink, hist,
-            max(offset + tb.countNew, trimmedMax, int(lut.max()) if n else 0) + 1)
+            max(offset + tb.countNew, trimmedMax, int(lut.max()) if n else 0) + 1, deferred,
+            max(offset, trimmedMax) + 1)
         self.mark('tile %d,%d window delivered' % (tile.col, tile.row))
         # the neighbours' labels are no longer needed once both users have run
         for nb in (up, lf):
@@ -812,10 +824,13 @@ class TiledSegmenter(object):
         return max(offset, trimmedMax)
 
     # ---- driver ----------------------------------------------------------------------------
-    def run(self, sink, comm=None):
+    def run(self, sink, comm=None, deferFinal=False):
         """Segment and stitch every tile; returns (maxSegId, histogram).  With a communicator of
         more than one rank (distributed.TorchComm) the tiles are shared out over the ranks and
-        `sink` receives this rank's trimmed windows only."""
+        `sink` receives this rank's trimmed windows only.  deferFinal: return as soon as the
+        histogram is on the host, possibly with the last window still on its way to the sink; the
+        caller must then call finish() before it touches the output."""
+        self.inFlight = None
         if comm is not None and comm.world > 1:
             return self.runSharded(sink, comm)
         cfg = self.cfg
@@ -847,8 +862,10 @@ class TiledSegmenter(object):
                         th.start()
                         workers.append(th)
             with self.timings.interval('stitchtiles') if numWorkers > 0 else _nullContext():
+                deferred = []
                 for cr in self.order:
                     tile = self.tiles[cr]
+                    last = deferred if cr == self.order[-1] else None
                     if numWorkers > 0:
                         if not tile.done.wait(cfg.tileCompletionTimeout):
                             self.forceExit.set()
@@ -857,14 +874,22 @@ class TiledSegmenter(object):
                         if tile.error is not None:
                             raise PyShepSegTilingError("A segmentation worker failed on tile "
                                 "col={} row={}: {}".format(tile.col, tile.row, tile.error))
-                        offset = self.stitchOne(main, pool, tile, offset, sink, hist)
+                        offset = self.stitchOne(main, pool, tile, offset, sink, hist, last)
                     else:
                         if self.verbose:
                             print("Doing tile row={}, col={}".format(tile.row, tile.col))
                         self.segmentOne(main, pool, tile)
                         with self.timings.interval('stitchtiles'):
-                            offset = self.stitchOne(main, pool, tile, offset, sink, hist)
-            histogram = hist.fetch(main.ctx, offset + 1)
+                            offset = self.stitchOne(main, pool, tile, offset, sink, hist, last)
+            if deferred:
+                # the histogram was queued ahead of the last window: it is here long before the window is
+                main.ctx.call('ssg_wait_mark', 0)
+                histogram = hist.collect()
+                self.inFlight = main
+                if not deferFinal:
+                    self.finish()
+            else:
+                histogram = hist.fetch(main.ctx, offset + 1)
             self.d2hBytes += histogram.nbytes
         finally:
             self.forceExit.set()
@@ -882,6 +907,12 @@ class TiledSegmenter(object):
                 main.lock.release()
         return (offset, histogram)
 
+
+    def finish(self):
+        """Wait for the last window of a run(deferFinal=True) to land in the sink."""
+        if getattr(self, 'inFlight', None) is not None:
+            self.inFlight.ctx.call('ssg_wait_mark', 1)
+            self.inFlight = None
 
     def runSharded(self, sink, comm):
         """
@@ -1088,6 +1119,8 @@ class _DeviceHistogram(object):
     def __init__(self):
         self.dev = None
         self.cap = 0
+        self.pinned = None
+        (self.pending, self.pendingLen) = (0, 0)
 
     def ensure(self, ctx, n):
         if n <= self.cap:
@@ -1115,10 +1148,31 @@ class _DeviceHistogram(object):
             h[0] = 0     # the null count is always removed (tiling.py:1930-1931)
         return h.astype(numpy.float64)
 
+    def fetchAsync(self, ctx, n):
+        """Queue the copy of the first n bins into pinned memory (no wait); collect() converts"""
+        if self.pinned is None or self.pinned.array.size < n:
+            if self.pinned is not None:
+                self.pinned.free()
+            self.pinned = _lib.PinnedArray((max(n, 1 << 20),), numpy.uint64)
+        self.pending = min(n, self.cap) if self.dev is not None else 0
+        self.pendingLen = n
+        if self.pending > 0:
+            ctx.call('ssg_memcpy_d2h_async', _lib.ptr(self.pinned.array), self.dev, self.pending * 8)
+
+    def collect(self):
+        h = numpy.zeros(self.pendingLen, dtype=numpy.float64)
+        h[:self.pending] = self.pinned.array[:self.pending]
+        if self.pendingLen > 0:
+            h[0] = 0
+        return h
+
     def close(self, ctx):
         if self.dev is not None:
             ctx.dev_free(self.dev)
             self.dev = None
+        if self.pinned is not None:
+            self.pinned.free()
+            self.pinned = None
 
 
 def estimateStatsFromHisto(sink, hist):
@@ -1229,13 +1283,14 @@ def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
             imgNullVal, fourConnected, minSegmentSize, shepseg.spectralThreshold(msd),
             simpleTileRecode, concurrencyCfg, timings, verbose)
         seg.mark('run start')
-        (maxSegId, hist) = seg.run(sink, comm)
+        (maxSegId, hist) = seg.run(sink, comm, deferFinal=True)
         seg.mark('run done')
         if len(hist) > 0:          # (ranks other than 0 of a sharded run hold no histogram)
             if writeHistogram:
                 sink.writeHistogram(hist)
             result.hasEmptySegments = checkForEmptySegments(hist, overlapSize)
             estimateStatsFromHisto(sink, hist)
+        seg.finish()          # (the last window travelled while the statistics were worked out)
         seg.mark('histogram and statistics written')
         if returnGDALDS:
             result.outDs = getattr(sink, 'ds', sink)
