@@ -268,7 +268,9 @@ k_number_roots(const unsigned *__restrict__ label, int64_t N, const unsigned *__
 // ids of the roots to every pixel + the size table.  A root whose later neighbours (right and
 // below; a root is the raster-first pixel of its clump) do not point at it is a clump of one
 // pixel: those are listed for the single-pixel stage, which then needs no scan of its own.
-#define GATHER_PIX 1024   // pixels per block (4 strips of 256)
+// A thread takes four consecutive pixels (16-byte loads and stores); sizes go up by one atomic per
+// run of equal ids inside the thread, a single-pixel clump by a plain store.
+#define GATHER_PIX 1024   // pixels per block (256 threads x 4)
 __global__ void __launch_bounds__(256)
 k_gather_ids(const unsigned *__restrict__ label, int64_t nRows, int64_t nCols, int four,
              unsigned *seg, unsigned *segSize, unsigned *singles, unsigned long long *counters)
@@ -279,42 +281,74 @@ k_gather_ids(const unsigned *__restrict__ label, int64_t nRows, int64_t nCols, i
     const int64_t N = nRows * nCols;
     if (threadIdx.x == 0) sCount = 0;
     __syncthreads();
+    const int64_t p0 = (int64_t)blockIdx.x * GATHER_PIX + (int64_t)threadIdx.x * 4;
+    unsigned l[4], id[4];
+    bool single[4] = {false, false, false, false};
+    const bool vec = p0 + 4 <= N && (N % 4 == 0);
+    if (vec) {
+        const uint4 lv = *reinterpret_cast<const uint4 *>(label + p0);
+        l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+    } else {
 #pragma unroll
-    for (int it = 0; it < GATHER_PIX / 256; it++) {
-        const int64_t p = (int64_t)blockIdx.x * GATHER_PIX + it * 256 + threadIdx.x;
-        unsigned id = 0;
-        const bool valid = p < N;
-        bool single = false;
-        if (valid) {
-            const unsigned l = label[p];
-            if (l == SSG_NIL) id = 0;
-            else if (l == (unsigned)p) id = seg[p];
-            else id = __ldcg(seg + l);   // written by k_number_roots (previous launch)
-            if (l != (unsigned)p) seg[p] = id;
-            else if (singles) {
-                const int64_t y = p / nCols, x = p % nCols;
+        for (int i = 0; i < 4; i++) l[i] = p0 + i < N ? label[p0 + i] : SSG_NIL;
+    }
+    unsigned nextLabel = SSG_NIL;      // label of the pixel after my four (same row or not: checked below)
+    bool anyRoot = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) anyRoot |= (p0 + i < N && l[i] == (unsigned)(p0 + i));
+    if (anyRoot && p0 + 4 < N) nextLabel = label[p0 + 4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t p = p0 + i;
+        id[i] = 0;
+        if (p >= N || l[i] == SSG_NIL) continue;
+        if (l[i] == (unsigned)p) {
+            id[i] = seg[p];            // written by k_number_roots (previous launch)
+            if (singles) {
+                const int64_t y = p / nCols, x = p - y * nCols;
                 const bool hasR = x + 1 < nCols, hasD = y + 1 < nRows;
-                bool grown = (hasR && label[p + 1] == l) || (hasD && label[p + nCols] == l);
+                const unsigned right = i < 3 ? l[i + 1 < 4 ? i + 1 : 3] : nextLabel;
+                bool grown = (hasR && right == l[i]) || (hasD && label[p + nCols] == l[i]);
                 if (!four && hasD)
-                    grown = grown || (x > 0 && label[p + nCols - 1] == l) || (hasR && label[p + nCols + 1] == l);
-                single = !grown;
+                    grown = grown || (x > 0 && label[p + nCols - 1] == l[i]) || (hasR && label[p + nCols + 1] == l[i]);
+                single[i] = !grown;
             }
+        } else {
+            id[i] = __ldcg(seg + l[i]);
         }
-        if (singles) {     // block-local list first: one global atomic per block
-            const unsigned m = __ballot_sync(0xffffffffu, single);
-            unsigned base = 0;
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                if ((int)lane_id() == leader) base = atomicAdd(&sCount, (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (single) sList[base + __popc(m & ((1u << lane_id()) - 1u))] = (unsigned)p;
-            }
+    }
+    if (vec) *reinterpret_cast<uint4 *>(seg + p0) = make_uint4(id[0], id[1], id[2], id[3]);
+    else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (p0 + i < N) seg[p0 + i] = id[i];
+    }
+    // sizes: one update per run of equal ids among my four pixels
+    unsigned n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (p0 + i >= N) break;
+        n++;
+        const bool last = i == 3 || p0 + i + 1 >= N || id[i + 1 < 4 ? i + 1 : 3] != id[i];
+        if (last) {
+            if (single[i]) segSize[id[i]] = 1u;      // nobody else touches a one-pixel clump's size
+            else atomicAdd(&segSize[id[i]], n);
+            n = 0;
         }
-        // size histogram: one atomic per run of equal ids in the warp
-        const WarpRuns run = warp_runs(id, valid);
-        if (run.head) atomicAdd(&segSize[id], run.len);
     }
     if (!singles) return;
+    // block-local list of the single-pixel clumps first: one global atomic per block
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const unsigned m = __ballot_sync(0xffffffffu, single[i]);
+        if (m) {
+            unsigned base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)lane_id() == leader) base = atomicAdd(&sCount, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (single[i]) sList[base + __popc(m & ((1u << lane_id()) - 1u))] = (unsigned)(p0 + i);
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0 && sCount) sBase = atomicAdd(&counters[C_NUM_SINGLEPIX], (unsigned long long)sCount);
     __syncthreads();

@@ -67,6 +67,8 @@ __device__ __forceinline__ void extents_mark(const StitchTables &tb, unsigned s,
     const bool rowInTrim = r >= top && r < bottom;
     const bool touchesTrim = rowInTrim && cEnd >= left && c < right;
     const bool allInTrim = rowInTrim && c >= left && cEnd < right;
+    // (plain stores: looking first, to skip a store when the byte is set already, was measured --
+    // the byte loads cost twice what the stores do)
     if (touchesTrim) tb.interior[s] = 1;
     if (!allInTrim) {
         // the frame around the trimmed window (a few percent of the pixels)
@@ -390,6 +392,35 @@ k_apply_lut_window(const unsigned *__restrict__ tile, int64_t xsize, const unsig
     if (run.head) atomicAdd(&hist[v], (unsigned long long)run.len);
 }
 
+// the same with four consecutive pixels of a row per thread (window width, strides and offsets
+// multiples of four; 16-byte loads and stores; one histogram atomic per run inside the thread)
+__global__ void __launch_bounds__(256)
+k_apply_lut_window4(const unsigned *__restrict__ tile, int64_t xsize, const unsigned *__restrict__ lut,
+                    int64_t top, int64_t left, int64_t wRows, int64_t wCols, unsigned *out,
+                    int64_t outStride, unsigned long long *hist, int64_t histLen)
+{
+    const int64_t quadsPerRow = wCols / 4;
+    const int64_t nQuads = wRows * quadsPerRow;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nQuads; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = g / quadsPerRow, c = (g - r * quadsPerRow) * 4;
+        uint4 v = *reinterpret_cast<const uint4 *>(tile + (r + top) * xsize + (c + left));
+        v.x = __ldg(lut + v.x); v.y = __ldg(lut + v.y); v.z = __ldg(lut + v.z); v.w = __ldg(lut + v.w);
+        *reinterpret_cast<uint4 *>(out + r * outStride + c) = v;
+        if (hist) {
+            const unsigned s[4] = {v.x, v.y, v.z, v.w};
+            unsigned n = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                n++;
+                if (i == 3 || s[i + 1 < 4 ? i + 1 : 3] != s[i]) {
+                    if ((int64_t)s[i] < histLen) atomicAdd(&hist[s[i]], (unsigned long long)n);
+                    n = 0;
+                }
+            }
+        }
+    }
+}
+
 extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
                                     const uint32_t *lutHost, uint32_t maxId, int64_t top, int64_t bottom,
                                     int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
@@ -407,10 +438,20 @@ extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64
     SSG_CUDA(ctx, cudaMemcpyAsync(ctx->lut.p, ctx->lutStage.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t wRows = bottom - top, wCols = right - left;
     if (wRows * wCols > 0) {
+        const bool quads = wCols % 4 == 0 && xsize % 4 == 0 && left % 4 == 0 && outStride % 4 == 0 &&
+                           (uintptr_t)tileDev % 16 == 0 && (uintptr_t)outDev % 16 == 0;
         SSG_PROF_BEGIN(ctx, "k_apply_lut_window");
-        k_apply_lut_window<<<gridFor(wRows * wCols, 256), 256, 0, ctx->stream>>>(
-            tileDev, xsize, bufp<unsigned>(ctx->lut), top, left, wRows, wCols, outDev, outStride,
-            reinterpret_cast<unsigned long long *>(histDev), histLen);
+        if (quads) {
+            int64_t blocks = (wRows * wCols / 4 + 255) / 256;
+            if (blocks > (int64_t)ctx->numSMs * 16) blocks = (int64_t)ctx->numSMs * 16;
+            k_apply_lut_window4<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                tileDev, xsize, bufp<unsigned>(ctx->lut), top, left, wRows, wCols, outDev, outStride,
+                reinterpret_cast<unsigned long long *>(histDev), histLen);
+        } else {
+            k_apply_lut_window<<<gridFor(wRows * wCols, 256), 256, 0, ctx->stream>>>(
+                tileDev, xsize, bufp<unsigned>(ctx->lut), top, left, wRows, wCols, outDev, outStride,
+                reinterpret_cast<unsigned long long *>(histDev), histLen);
+        }
         SSG_LAUNCHED(ctx);
     }
     return SSG_OK;
