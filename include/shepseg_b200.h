@@ -172,6 +172,27 @@ int ssg_download_labels(ssg_ctx *ctx, uint32_t *segOutHost);
 /* device pointer of the resident labels of the last tile (owned by the context) */
 uint32_t *ssg_resident_labels(ssg_ctx *ctx);
 
+/* ---- spectral-cluster fit: the KMeans.fit call of shepseg.fitSpectralClusters
+ *      (shepseg.py:252-314; tiling.fitSpectralClustersWholeFile, tiling.py:154-226) --------
+ * The two steps of a Lloyd iteration as scikit-learn runs them ("lloyd" algorithm, float64), on
+ * the device; the loop around them (stop when no label changes, when the summed squared centre
+ * shift is <= tol, or after max_iter iterations) and the relocation of empty clusters are the
+ * host's (pyshepseg_b200.shepseg._fitOnDevice).  X is the host sample matrix (n x nBands,
+ * row-major), centres the initial centres (k x nBands).  Not bit identical to scikit-learn (order
+ * of the sums, ties): centres agree to a tolerance stated in the tests.  One fit at a time per
+ * host thread. */
+int ssg_kmeans_begin(ssg_ctx *ctx, const double *X, int64_t n, int nBands, const double *centres, int k);
+/* the assignment step with the current centres: samples per cluster, inertia, labels changed */
+int ssg_kmeans_step(ssg_ctx *ctx, uint64_t *countsOut, double *inertia, uint64_t *changed);
+/* labels of the last step (host, n) -- only needed when a cluster came out empty */
+int ssg_kmeans_labels(ssg_ctx *ctx, int32_t *labelsOut);
+/* sample farIdx[i] becomes the only member of empty cluster emptyIds[i] (scikit-learn's
+ * _relocate_empty_clusters_dense; which samples is decided on the host with numpy, as there) */
+int ssg_kmeans_relocate(ssg_ctx *ctx, int m, const int64_t *farIdx, const int32_t *emptyIds);
+/* centres = mean of the samples assigned by the last step; summed squared shift; new centres (optional) */
+int ssg_kmeans_update(ssg_ctx *ctx, double *shift, double *centresOut);
+int ssg_kmeans_centres(ssg_ctx *ctx, double *centresOut);
+
 /* ---- tile stitching: tiling.stitchTiles / recodeTile / recodeSharedSegments /
  *      relabelSegments / crossesMidline (tiling.py:950-1306) --------------------------
  *

@@ -108,6 +108,12 @@ SIGNATURES = {
     'ssg_memcpy2d_d2h_async': (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     'ssg_mark': (_i, [_vp, _i]),
     'ssg_wait_mark': (_i, [_vp, _i]),
+    'ssg_kmeans_begin': (_i, [_vp, _vp, _i64, _i, _vp, _i]),
+    'ssg_kmeans_step': (_i, [_vp, _vp, _c.POINTER(_dbl), _c.POINTER(_c.c_uint64)]),
+    'ssg_kmeans_labels': (_i, [_vp, _vp]),
+    'ssg_kmeans_relocate': (_i, [_vp, _i, _vp, _vp]),
+    'ssg_kmeans_update': (_i, [_vp, _c.POINTER(_dbl), _vp]),
+    'ssg_kmeans_centres': (_i, [_vp, _vp]),
     'ssg_launch_count': (_c.c_uint64, [_vp]),
     'ssg_profile_enable': (_i, [_vp, _i]),
     'ssg_profile_fetch': (_i, [_vp, _c.c_char_p, _sz]),

@@ -427,18 +427,20 @@ k_mark_unvisited(const unsigned *__restrict__ pix, int64_t M, unsigned *label)
 // One warp replays the reference's capped flood fill over one region (shepseg.py:490-539).
 // Lane l looks at window cell (cx, cy) = (sx-1 + l/3, sy-1 + l%3): columns outer, rows inner,
 // which is the order the reference pushes neighbours in (shepseg.py:523-524).
-__global__ void __launch_bounds__(128)
+// (one warp per block, the LIFO stack in shared memory: the fill is a chain of dependent steps --
+// pop, look at the 3x3 window, push -- and a stack in global memory doubled the length of each)
+__global__ void __launch_bounds__(32)
 k_capped_fill(const int32_t *__restrict__ img, int64_t nRows, int64_t nCols, int four,
               const unsigned *__restrict__ sortedPix, const unsigned *__restrict__ runStart,
-              unsigned numRuns, int64_t M, unsigned *label, unsigned *stackPool, unsigned stackCap)
+              unsigned numRuns, int64_t M, unsigned *label)
 {
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ unsigned stack[SSG_MAX_CLUMP_SIZE + 32];
+    const unsigned warp = blockIdx.x;
     if (warp >= numRuns) return;
     const unsigned lane = lane_id();
     const int64_t lo = runStart[warp];
     const int64_t hi = (warp + 1 < numRuns) ? (int64_t)runStart[warp + 1] : M;
     volatile unsigned *vlabel = label;
-    unsigned *stack = stackPool + (size_t)warp * stackCap;
     const int dx = (int)(lane / 3) - 1, dy = (int)(lane % 3) - 1;
     const bool cellUsed = lane < 9 && (!four || dx == 0 || dy == 0);
 
@@ -499,12 +501,8 @@ static int split_oversized(ssg_ctx *ctx, const int32_t *img, int64_t nRows, int6
     SSG_PROF_BEGIN(ctx, "k_mark_unvisited");
     k_mark_unvisited<<<gridFor(M, 256), 256, 0, ctx->stream>>>(pixSorted, M, label);
     SSG_LAUNCHED(ctx);
-    const unsigned stackCap = SSG_MAX_CLUMP_SIZE + 32;
-    SSG_TRY(ssg_reserve(ctx, ctx->emuStack, (size_t)numRuns * stackCap * sizeof(unsigned)));
-    const unsigned warpsPerBlock = 4;
     SSG_PROF_BEGIN(ctx, "k_capped_fill");
-    k_capped_fill<<<(numRuns + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, 0, ctx->stream>>>(
-        img, nRows, nCols, four, pixSorted, runStart, numRuns, M, label, bufp<unsigned>(ctx->emuStack), stackCap);
+    k_capped_fill<<<numRuns, 32, 0, ctx->stream>>>(img, nRows, nCols, four, pixSorted, runStart, numRuns, M, label);
     SSG_LAUNCHED(ctx);
     return SSG_OK;
 }

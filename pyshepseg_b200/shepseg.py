@@ -168,11 +168,21 @@ def segmentTile(ctx, img, centres, imgNullVal, fourConnected, minSegmentSize, th
     return res
 
 
-def fitSpectralClusters(img, numClusters, subsamplePcnt, imgNullVal, fixedKMeansInit):
+# Where the k-means fit runs: 'sklearn' (scikit-learn on the host, exactly the reference's call)
+# or 'gpu' (Lloyd iterations on the device, ssg_kmeans_lloyd: same algorithm, centres equal to
+# scikit-learn's within a tolerance, orders of magnitude faster on a million samples).  The
+# environment variable SSG_KMEANS overrides the module default.
+KMEANS_BACKEND = 'sklearn'
+
+
+def fitSpectralClusters(img, numClusters, subsamplePcnt, imgNullVal, fixedKMeansInit, backend=None,
+        context=None):
     """
     First step of Shepherd segmentation (shepseg.py:252-314): k-means on a subsample of the
-    non-null pixels.  Host side, scikit-learn, as in the reference.
+    non-null pixels.  Returns a fitted sklearn.cluster.KMeans object either way; `backend`
+    ('sklearn' / 'gpu', default KMEANS_BACKEND or $SSG_KMEANS) says who runs the iterations.
     """
+    import os
     from sklearn.cluster import KMeans
     img = numpy.asarray(img)
     nBands = img.shape[0]
@@ -180,12 +190,99 @@ def fitSpectralClusters(img, numClusters, subsamplePcnt, imgNullVal, fixedKMeans
     if imgNullVal is not None:
         pixels = pixels[(pixels != imgNullVal).all(axis=1)]
     sample = pixels[::int(round(100. / subsamplePcnt))]
+    if backend is None:
+        backend = os.environ.get('SSG_KMEANS', KMEANS_BACKEND)
+    if backend == 'gpu':
+        return _fitOnDevice(sample, numClusters, fixedKMeansInit, context)
     if fixedKMeansInit:
         km = KMeans(n_clusters=numClusters, n_init=1,
             init=diagonalClusterCentres(sample, numClusters))
     else:
         km = KMeans(n_clusters=numClusters, n_init=5, init='k-means++')
     km.fit(sample)
+    return km
+
+
+def _lloydOnDevice(ctx, X, centres, maxIter, tol):
+    """
+    The loop of scikit-learn's _kmeans_single_lloyd around the two device steps: assignment
+    (ssg_kmeans_step), relocation of empty clusters as scikit-learn does it (the n_empty samples
+    farthest from their centres, picked with the same numpy.argpartition expression, each becomes
+    the sole member of an empty cluster), update (ssg_kmeans_update); stop when the labels repeat
+    or the summed squared centre shift is <= tol.  Returns (centres, inertia, iterations).
+    """
+    (n, k) = (X.shape[0], centres.shape[0])
+    ctx.call('ssg_kmeans_begin', _lib.ptr(X), n, X.shape[1], _lib.ptr(centres), k)
+    counts = numpy.zeros(k, dtype=numpy.uint64)
+    inertia = ctypes.c_double(0.0)
+    changed = ctypes.c_uint64(0)
+    shift = ctypes.c_double(0.0)
+    cur = numpy.array(centres)
+    strict = False
+    it = 0
+    for it in range(1, maxIter + 1):
+        ctx.call('ssg_kmeans_step', _lib.ptr(counts), ctypes.byref(inertia), ctypes.byref(changed))
+        empty = numpy.flatnonzero(counts == 0)
+        if len(empty) > 0:
+            labels = numpy.empty(n, dtype=numpy.int32)
+            ctx.call('ssg_kmeans_labels', _lib.ptr(labels))
+            ctx.call('ssg_kmeans_centres', _lib.ptr(cur))       # the centres this step assigned to
+            distances = ((X - cur[labels]) ** 2).sum(axis=1)
+            far = numpy.argpartition(distances, -len(empty))[:-len(empty) - 1:-1].astype(numpy.int64)
+            ctx.call('ssg_kmeans_relocate', len(empty), _lib.ptr(numpy.ascontiguousarray(far)),
+                _lib.ptr(numpy.ascontiguousarray(empty.astype(numpy.int32))))
+        ctx.call('ssg_kmeans_update', ctypes.byref(shift), None)
+        if changed.value == 0:
+            strict = True
+            break
+        if shift.value <= tol:
+            break
+    ctx.call('ssg_kmeans_centres', _lib.ptr(cur))
+    if not strict:
+        # (scikit-learn assigns once more so that the inertia belongs to the final centres)
+        ctx.call('ssg_kmeans_step', None, ctypes.byref(inertia), ctypes.byref(changed))
+    return (cur, float(inertia.value), it)
+
+
+def _fitOnDevice(sample, numClusters, fixedKMeansInit, context=None, maxIter=300, tol=1e-4):
+    """
+    scikit-learn's KMeans.fit restated around ssg_kmeans_lloyd: the data are centred on their mean
+    (as scikit-learn does, for the arithmetic), tol is scaled by the mean feature variance, the
+    initial centres are the diagonal ones (fixedKMeansInit) or scikit-learn's own k-means++ draw,
+    five of them, keeping the fit with the lowest inertia.  The result is a scikit-learn KMeans
+    object carrying the fitted centres, so predict() and everything else work as usual.
+    """
+    from sklearn.cluster import KMeans, kmeans_plusplus
+    ctx = context if context is not None else _lib.default_context()
+    X = numpy.ascontiguousarray(sample, dtype=numpy.float64)
+    if X.shape[0] < numClusters:
+        raise ValueError('n_samples=%d should be >= n_clusters=%d' % (X.shape[0], numClusters))
+    mean = X.mean(axis=0)
+    Xc = X - mean
+    absTol = float(numpy.mean(numpy.var(Xc, axis=0)) * tol)
+    if fixedKMeansInit:
+        inits = [numpy.asarray(diagonalClusterCentres(sample, numClusters), dtype=numpy.float64)]
+    else:
+        rs = numpy.random.RandomState()
+        inits = [kmeans_plusplus(X, numClusters, random_state=rs)[0] for _ in range(5)]
+    best = None
+    for init in inits:
+        centres = numpy.ascontiguousarray(init - mean, dtype=numpy.float64)
+        (centres, inertia, nIter) = _lloydOnDevice(ctx, Xc, centres, int(maxIter), absTol)
+        if best is None or inertia < best[1]:
+            best = (centres + mean, inertia, nIter)
+    (centres, inertia, nIter) = best
+    # a fitted scikit-learn object around those centres (fit on the centres themselves: trivially
+    # converged; then the attributes are set to what the device computed)
+    km = KMeans(n_clusters=numClusters, n_init=1, init=centres, max_iter=1)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        km.fit(centres)
+    km.cluster_centers_ = numpy.ascontiguousarray(centres, dtype=numpy.float64)
+    km.inertia_ = float(inertia)
+    km.n_iter_ = int(nIter)
+    km.labels_ = None
     return km
 
 

@@ -314,3 +314,58 @@ def test_assign_pruning_grid_equals_full_scan_and_oracle(shepseg, case):
         finally:
             del os.environ['SSG_ASSIGN_GRID']
         same(got, full, 'pruned assignment vs full scan (null %s)' % nullVal)
+
+
+@pytest.mark.parametrize('bands,k', [(4, 60), (3, 12), (10, 30)])
+def test_gpu_lloyd_iterations_equal_sklearn(shepseg, bands, k):
+    """The Lloyd iterations on the device (ssg_kmeans_lloyd; shepseg.py:252-314, f3 of SURVEY.md
+    section 8) are scikit-learn's: from the same initial centres, after the same number of
+    iterations, the centres agree to 1e-9 of the data range (float64, another summation order)."""
+    from sklearn.cluster import KMeans
+    img = synth.synth_v1(400, 500, bands, seed=bands)
+    sample = numpy.moveaxis(img, 0, -1).reshape(-1, bands)[::7]
+    init = shepseg.diagonalClusterCentres(sample, k)
+    span = float(img.max()) - float(img.min())
+    for iters in (1, 5, 20):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref = KMeans(n_clusters=k, n_init=1, init=init, max_iter=iters, tol=0.0).fit(sample)
+        got = shepseg._fitOnDevice(sample, k, True, maxIter=iters, tol=0.0)
+        err = numpy.abs(got.cluster_centers_ - ref.cluster_centers_).max()
+        assert err <= 1e-9 * span, '%d iterations: centres differ by %g (data range %g)' % (iters, err, span)
+        assert abs(got.inertia_ - ref.inertia_) <= 1e-9 * ref.inertia_
+
+
+def test_gpu_lloyd_fit_converges_to_sklearn_centres(shepseg):
+    """On data with real clusters both fits converge, to the same centres: stated tolerance 1e-6
+    of the data range (the north star's "centres within a stated tolerance"); the object that
+    comes back is a fitted scikit-learn KMeans and assigns pixels like scikit-learn's own."""
+    rng = numpy.random.default_rng(5)
+    k = 12
+    true = rng.uniform(500, 9000, (k, 4))
+    lab = rng.integers(0, k, 300 * 320)
+    img = numpy.clip(numpy.rint(true[lab] + rng.normal(0, 40, (len(lab), 4))), 1, 65534).astype(numpy.uint16)
+    img = numpy.ascontiguousarray(img.T.reshape(4, 300, 320))
+    ref = shepseg.fitSpectralClusters(img, k, 20, None, True, backend='sklearn')
+    got = shepseg.fitSpectralClusters(img, k, 20, None, True, backend='gpu')
+    span = float(img.max()) - float(img.min())
+    err = numpy.abs(got.cluster_centers_ - ref.cluster_centers_).max()
+    assert err <= 1e-6 * span, 'centres differ by %g (data range %g)' % (err, span)
+    assert abs(got.inertia_ - ref.inertia_) <= 1e-9 * ref.inertia_
+    pix = numpy.moveaxis(img[:, :50, :50], 0, -1).reshape(-1, 4)
+    assert numpy.array_equal(got.predict(pix), ref.predict(pix))
+    a = shepseg.doShepherdSegmentation(img, numClusters=k, minSegmentSize=20, kmeansObj=got)
+    b = shepseg.doShepherdSegmentation(img, numClusters=k, minSegmentSize=20, kmeansObj=ref)
+    assert numpy.array_equal(a.segimg, b.segimg)
+
+
+def test_gpu_lloyd_fit_kmeanspp_and_nulls(shepseg):
+    """k-means++ starts (five, the best kept) cannot be compared centre by centre with another
+    random draw: the inertia must be in scikit-learn's range; null pixels stay out of the sample"""
+    img = synth.synth_v1(500, 500, 3, seed=11, nullFrac=0.2)
+    ref = shepseg.fitSpectralClusters(img, 20, 10, 0, False, backend='sklearn')
+    got = shepseg.fitSpectralClusters(img, 20, 10, 0, False, backend='gpu')
+    assert got.cluster_centers_.shape == (20, 3)
+    assert got.inertia_ <= 1.05 * ref.inertia_
+    assert (got.cluster_centers_.min(axis=0) > 0).all()      # no centre pulled to the null value
