@@ -39,6 +39,8 @@ extern "C" {
 #define SSG_U8 0
 #define SSG_U16 1
 #define SSG_I16 2
+#define SSG_U32 3      /* per-segment statistics only (ssg_segment_stats) */
+#define SSG_I32 4
 
 #define SSG_OK 0
 #define SSG_ERR_ARG 1       /* bad argument (shape, dtype, null pointer, too many bands) */
@@ -192,6 +194,25 @@ int ssg_kmeans_relocate(ssg_ctx *ctx, int m, const int64_t *farIdx, const int32_
 /* centres = mean of the samples assigned by the last step; summed squared shift; new centres (optional) */
 int ssg_kmeans_update(ssg_ctx *ctx, double *shift, double *centresOut);
 int ssg_kmeans_centres(ssg_ctx *ctx, double *centresOut);
+
+/* ---- per-segment statistics: tilingstats.calcPerSegmentStatsTiled (tilingstats.py:85-215),
+ *      accumulateSegDict (467-517), SegmentStats (923-1008) ---------------------------------
+ * Statistics of one image band over the segments of a label raster of the same shape.  seg and
+ * img are device pointers when onDevice (labels that are still resident), host pointers
+ * otherwise.  Pixels of segment 0 and pixels equal to nullVal (when hasNull) do not count.
+ * statIds: 0 min, 1 max, 2 mean, 3 stddev, 4 median, 5 mode, 6 percentile (params[i] = the
+ * percentile), 7 pixcount -- the reference's STATID_* (tilingstats.py:770-777).  mean and
+ * stddev go to float32 columns, the others to int64 columns (RatPage, tilingstats.py:1972-1996),
+ * numbered in the order given: intOut is (number of int statistics, maxSegId + 1) row-major,
+ * floatOut likewise.  A segment without valid pixels gets `missing` everywhere except in a
+ * pixcount column (0, SegmentStats.getStat, 1006-1007); row 0 is zero.  totalOut (maxSegId + 1,
+ * may be NULL) receives every segment's pixel count with the null-valued pixels included -- what
+ * the reference compares with the Histogram column to decide a segment is complete
+ * (checkSegComplete, 519-554).  A label above maxSegId is an error. */
+int ssg_segment_stats(ssg_ctx *ctx, const uint32_t *seg, const void *img, int dtype, int64_t nPixels,
+                      int onDevice, int hasNull, int64_t nullVal, uint32_t maxSegId, int nStats,
+                      const int32_t *statIds, const int32_t *params, int64_t missing,
+                      int64_t *intOut, float *floatOut, uint32_t *totalOut);
 
 /* ---- tile stitching: tiling.stitchTiles / recodeTile / recodeSharedSegments /
  *      relabelSegments / crossesMidline (tiling.py:950-1306) --------------------------

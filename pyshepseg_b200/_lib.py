@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(_HERE, 'libshepseg_b200.so')
 
 SSG_U8, SSG_U16, SSG_I16 = 0, 1, 2
+SSG_U32, SSG_I32 = 3, 4      # per-segment statistics only
 DTYPE_CODES = {
     numpy.dtype(numpy.uint8): SSG_U8,
     numpy.dtype(numpy.uint16): SSG_U16,
@@ -114,6 +115,7 @@ SIGNATURES = {
     'ssg_kmeans_relocate': (_i, [_vp, _i, _vp, _vp]),
     'ssg_kmeans_update': (_i, [_vp, _c.POINTER(_dbl), _vp]),
     'ssg_kmeans_centres': (_i, [_vp, _vp]),
+    'ssg_segment_stats': (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i64, _u32, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     'ssg_launch_count': (_c.c_uint64, [_vp]),
     'ssg_profile_enable': (_i, [_vp, _i]),
     'ssg_profile_fetch': (_i, [_vp, _c.c_char_p, _sz]),

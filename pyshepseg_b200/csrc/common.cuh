@@ -276,7 +276,7 @@ static inline int ssg_fetch_counters(ssg_ctx *ctx)
     return SSG_OK;
 }
 
-static inline size_t dtypeSize(int dt) { return dt == SSG_U8 ? 1 : 2; }
+static inline size_t dtypeSize(int dt) { return dt == SSG_U8 ? 1 : (dt == SSG_U32 || dt == SSG_I32) ? 4 : 2; }
 
 // ---- device helpers ----------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

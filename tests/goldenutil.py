@@ -26,7 +26,7 @@ def single_tile_names():
     names = []
     for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))):
         n = os.path.basename(p)[:-4]
-        if n.startswith('tiled_') or n == 'clump_only':
+        if n.startswith(('tiled_', 'stats_')) or n == 'clump_only':
             continue
         names.append(n)
     return names
