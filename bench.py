@@ -599,6 +599,54 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         sameMosaic = bool(t.item())
 
+    # ---- N ranks against one: the host-to-host mosaic of the last timed step, its windows put
+    # together from all ranks, against rank 0 segmenting the same raster alone (untimed)
+    vsOneRank = None
+    if dist is not None and not args.no_parity:
+        import zlib
+        bounds = [None] * world
+        dist.all_gather_object(bounds, (y0, y1))
+        bandT = torch.from_numpy(img.view(numpy.int16)).cuda()
+        full = None
+        if rank == 0:
+            full = torch.empty((nB, nR, nC), dtype=torch.int16, device='cuda')
+            full[:, y0:y1] = bandT
+            for r in range(1, world):
+                tmp = torch.empty((nB, bounds[r][1] - bounds[r][0], nC), dtype=torch.int16, device='cuda')
+                dist.recv(tmp.view(torch.uint8), r)      # (NCCL has no 16-bit integer type)
+                full[:, bounds[r][0]:bounds[r][1]] = tmp
+                del tmp
+        else:
+            dist.send(bandT.view(torch.uint8), 0)
+        del bandT
+        part = torch.zeros((nR, nC), dtype=torch.int32, device='cuda')
+        for (cr, (x, y, xs, ys)) in tileInfo.tiles.items():
+            if owner[cr] != rank:
+                continue
+            (top, bottom, left, right) = tiling.tileMargins(tileInfo, cr[0], cr[1], xs, ys, wl['overlapSize'])
+            win = pinnedOut.array[y + top - y0:y + bottom - y0, x + left:x + right]
+            part[y + top:y + bottom, x + left:x + right] = torch.from_numpy(
+                numpy.ascontiguousarray(win).view(numpy.int32)).cuda()
+        dist.reduce(part, 0)
+        if rank == 0:
+            torch.cuda.synchronize()
+            one = torch.empty((nR, nC), dtype=torch.int32, device='cuda')
+            seg1 = tiling.TiledSegmenter(tiling.DeviceRaster(full.data_ptr(), nB, nR, nC, numpy.uint16),
+                range(1, nB + 1), tileInfo, wl['overlapSize'], centres, None, wl['fourConnected'],
+                wl['minSegmentSize'], thr, False, tiling.SegmentationConcurrencyConfig(devices=[local]),
+                timinghooks.Timers())
+            (max1, hist1) = seg1.run(tiling.DeviceMosaicSink(one.data_ptr(), nC, nR))
+            torch.cuda.synchronize()
+            histN = getattr(getattr(lastE2E[0], 'outDs', None), 'hist', None)
+            vsOneRank = {'equal': bool(torch.equal(part, one)) and int(max1) == int(lastE2E[1]),
+                'segments': int(max1), 'segments_n_ranks': int(lastE2E[1]),
+                'histogram_equal': None if histN is None else bool(numpy.array_equal(histN, numpy.asarray(hist1))),
+                'crc32': '%08x' % (zlib.crc32(one.cpu().numpy()) & 0xffffffff),
+                'what': 'e2e mosaic of the last timed step on %d ranks vs the same raster segmented by rank 0 alone' % world}
+            del one, full
+        del part
+        torch.cuda.empty_cache()
+
     perRank = None
     if dist is not None:      # every rank's host timers of its last steps, for the scaling analysis
         mineT = {'resident': dict((k, round(v['total'] * 1e3, 1)) for (k, v) in
@@ -714,7 +762,8 @@ def run_ours(args, wl):
             'roofline': roof, 'roofline_other': extra, 'kernels': kernels,
             'cpu_baseline': cpu, 'cpu_baseline_port': cpuPort, 'clocks': clocks,
             'parity_vs_oracle': None if parity is None else parity['equal'], 'parity': parity,
-            'mosaic_crc32': mosaicCrc,
+            'mosaic_crc32': mosaicCrc, 'parity_vs_one_rank': None if vsOneRank is None else vsOneRank['equal'],
+            'one_rank': vsOneRank,
             'segments_per_scene': int(lastRes[1]),
             'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastProf[0].stageMs.items()),
             'per_rank': perRank,

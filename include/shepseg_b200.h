@@ -278,6 +278,16 @@ int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, i
                          const uint32_t *lutHost, uint32_t maxId, int64_t top, int64_t bottom,
                          int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
                          uint64_t *histDev, int64_t histLen);
+/* The same with the lut put together on the device: lut[i] = offset + relHost[i] where
+ * relHost[i] != 0 (the rank of a segment the tile numbered itself, tiling.py:1264-1267;
+ * relHost NULL: every label numbers itself, the simple recode of tiling.py:1067-1092), then
+ * lut[crossLabelsHost[j]] = crossIdsHost[j] for the nCross segments that take a neighbour's id.
+ * Used when the offset is the last thing to become known (tiles sharded over several GPUs). */
+int ssg_apply_rel_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
+                             const uint32_t *relHost, uint32_t maxId, uint32_t offset, int64_t nCross,
+                             const uint32_t *crossLabelsHost, const uint32_t *crossIdsHost,
+                             int64_t top, int64_t bottom, int64_t left, int64_t right,
+                             uint32_t *outDev, int64_t outStride, uint64_t *histDev, int64_t histLen);
 
 /* ---- plain device memory helpers (so the Python side needs nothing but ctypes) -------- */
 int ssg_dev_alloc(ssg_ctx *ctx, size_t bytes, void **out);

@@ -96,6 +96,8 @@ SIGNATURES = {
     'ssg_tile_tables_fetch': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'ssg_apply_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _u32, _i64, _i64, _i64, _i64, _vp, _i64,
         _vp, _i64]),
+    'ssg_apply_rel_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _u32, _u32, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
+        _vp, _i64, _vp, _i64]),
     'ssg_dev_alloc': (_i, [_vp, _sz, _c.POINTER(_vp)]),
     'ssg_dev_free': (_i, [_vp, _vp]),
     'ssg_memcpy_h2d': (_i, [_vp, _vp, _vp, _sz]),

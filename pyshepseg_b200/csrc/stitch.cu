@@ -421,6 +421,29 @@ k_apply_lut_window4(const unsigned *__restrict__ tile, int64_t xsize, const unsi
     }
 }
 
+// lut = offset + rank where the tile numbered the segment itself (rel = rank there, 0 elsewhere;
+// rel == nullptr: every label numbers itself, the simple recode), then the ids of the crossing
+// segments over it
+__global__ void __launch_bounds__(256)
+k_rel_to_lut(unsigned *lut, int64_t n, unsigned offset, int identity)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned r = identity ? (unsigned)i : lut[i];
+    lut[i] = r ? r + offset : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_lut_overrides(unsigned *lut, const unsigned *__restrict__ labels, const unsigned *__restrict__ ids, int64_t m)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) lut[labels[i]] = ids[i];
+}
+
+static int apply_lut_window(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize, int64_t top,
+                            int64_t bottom, int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
+                            uint64_t *histDev, int64_t histLen);
+
 extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
                                     const uint32_t *lutHost, uint32_t maxId, int64_t top, int64_t bottom,
                                     int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
@@ -436,6 +459,49 @@ extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64
     SSG_TRY(ssg_reserve(ctx, ctx->lut, n * sizeof(unsigned)));
     ctx->lutStage.assign(lutHost, lutHost + n);
     SSG_CUDA(ctx, cudaMemcpyAsync(ctx->lut.p, ctx->lutStage.data(), n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    return apply_lut_window(ctx, tileDev, ysize, xsize, top, bottom, left, right, outDev, outStride, histDev, histLen);
+}
+
+extern "C" int ssg_apply_rel_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
+                                        const uint32_t *relHost, uint32_t maxId, uint32_t offset, int64_t nCross,
+                                        const uint32_t *crossLabelsHost, const uint32_t *crossIdsHost,
+                                        int64_t top, int64_t bottom, int64_t left, int64_t right,
+                                        uint32_t *outDev, int64_t outStride, uint64_t *histDev, int64_t histLen)
+{
+    if (!ctx) return SSG_ERR_ARG;
+    ctx->err.clear();
+    SSG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!tileDev || !outDev || nCross < 0 || (nCross && (!crossLabelsHost || !crossIdsHost)))
+        SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
+    if (top < 0 || left < 0 || bottom > ysize || right > xsize || top > bottom || left > right) SSG_FAIL(ctx, SSG_ERR_ARG, "bad window");
+    for (int64_t i = 0; i < nCross; i++)
+        if (crossLabelsHost[i] > maxId) SSG_FAIL(ctx, SSG_ERR_ARG, "crossing label %u above maxId %u", crossLabelsHost[i], maxId);
+    SSG_TRY(ssg_scratch_reset(ctx));
+    const int64_t n = (int64_t)maxId + 1;
+    SSG_TRY(ssg_reserve(ctx, ctx->lut, (size_t)(n + 2 * nCross + 2) * sizeof(unsigned)));
+    unsigned *lut = bufp<unsigned>(ctx->lut), *crossDev = lut + n;
+    ctx->lutStage.clear();
+    if (relHost) ctx->lutStage.assign(relHost, relHost + n);
+    const size_t relLen = ctx->lutStage.size();
+    ctx->lutStage.insert(ctx->lutStage.end(), crossLabelsHost, crossLabelsHost + nCross);
+    ctx->lutStage.insert(ctx->lutStage.end(), crossIdsHost, crossIdsHost + nCross);
+    if (relLen) SSG_CUDA(ctx, cudaMemcpyAsync(lut, ctx->lutStage.data(), relLen * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    if (nCross) SSG_CUDA(ctx, cudaMemcpyAsync(crossDev, ctx->lutStage.data() + relLen, (size_t)nCross * 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    SSG_PROF_BEGIN(ctx, "k_rel_to_lut");
+    k_rel_to_lut<<<gridFor(n, 256), 256, 0, ctx->stream>>>(lut, n, offset, relHost ? 0 : 1);
+    SSG_LAUNCHED(ctx);
+    if (nCross) {
+        SSG_PROF_BEGIN(ctx, "k_lut_overrides");
+        k_lut_overrides<<<gridFor(nCross, 256), 256, 0, ctx->stream>>>(lut, crossDev, crossDev + nCross, nCross);
+        SSG_LAUNCHED(ctx);
+    }
+    return apply_lut_window(ctx, tileDev, ysize, xsize, top, bottom, left, right, outDev, outStride, histDev, histLen);
+}
+
+static int apply_lut_window(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize, int64_t top,
+                            int64_t bottom, int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
+                            uint64_t *histDev, int64_t histLen)
+{
     const int64_t wRows = bottom - top, wCols = right - left;
     if (wRows * wCols > 0) {
         const bool quads = wCols % 4 == 0 && xsize % 4 == 0 && left % 4 == 0 && outStride % 4 == 0 &&

@@ -101,7 +101,8 @@ class TileTable(object):
             rel = numpy.where(numbered, self.rank, numpy.uint32(0)).astype(numpy.uint32)
             crossing = numpy.flatnonzero((self.flags & KEY_FLAGS) != 0)
             self._prepared = (rel, numbered.astype(numpy.uint32), crossing)
-            self.crossingInTrim = crossing[(self.flags[crossing] & _lib.SEG_INTRIM) != 0]
+            self.crossInTrimMask = (self.flags[crossing] & _lib.SEG_INTRIM) != 0
+            self.crossingInTrim = crossing[self.crossInTrimMask]
             self.cachedMaxRankInTrim = self.maxRankInTrim
             self.pairs()
         return self._prepared
@@ -171,47 +172,68 @@ class MissingTable(Exception):
 class LazyResolver(object):
     """
     Final ids from per-tile tables when the id offsets are known up front (offset of a tile = sum
-    of countNew over the tiles before it).  lut entries are computed on demand:
+    of countNew over the tiles before it), looked up per label:
       numbered segment           offset + rank                       (tiling.py:1264-1267)
       crossing segment           the mode of the final ids of the neighbour's labels under it,
                                  smallest id on ties, top overlap first, left overriding
                                  (tiling.py:1107-1121, 1194)
       anything else, and 0       0 (the segment belongs to a neighbour, tiling.py:1241)
+    Only the crossing segments (a few thousand per tile) are stored; nothing of a tile's full
+    length is computed here, so the work per tile is small enough for the thread that also
+    feeds the GPU.  ids are uint32, or uint64 for the symbolic offsets of ShardedStitch.
     """
-    UNKNOWN = numpy.uint32(0xFFFFFFFF)
-
-    def __init__(self, tables, offsets, simple=False):
+    def __init__(self, tables, offsets, simple=False, dtype=numpy.uint32):
         self.tables = tables
         self.offsets = offsets
         self.simple = simple
-        self.luts = {}
+        self.dtype = numpy.dtype(dtype)
+        self.UNKNOWN = self.dtype.type(numpy.iinfo(self.dtype).max)
+        self.cross = {}         # tile -> (labels of its crossing segments ascending, their ids)
+        self.scratch = {}       # tile -> bool array over its labels, all False between calls
         self.misses = 0         # look-ups that could not be answered yet
         self.remote = {}        # tile of another rank -> (labels ascending, their final ids)
         self.requests = {}      # tile of another rank -> [label arrays] still to be asked for
 
-    def _lutOf(self, cr):
-        """the tile's lut with everything that needs no neighbour filled in (one vectorised pass);
-        crossing segments start out unknown"""
-        if cr not in self.luts:
+    def _crossOf(self, cr):
+        if cr not in self.cross:
             if cr not in self.tables:
                 raise MissingTable(cr)
             tb = self.tables[cr]
-            off = numpy.uint32(self.offsets[cr])
             if self.simple:
-                lut = numpy.arange(tb.maxId + 1, dtype=numpy.uint32) + off
-                lut[0] = 0
+                crossing = numpy.zeros(0, dtype=numpy.int64)
             else:
-                (rel, isNumbered, crossing) = tb.prepare()
-                lut = rel + isNumbered * off
-                lut[crossing] = self.UNKNOWN
-            self.luts[cr] = lut
-        return self.luts[cr]
+                crossing = tb.prepare()[2]
+            self.cross[cr] = (crossing, numpy.full(len(crossing), self.UNKNOWN, dtype=self.dtype))
+        return self.cross[cr]
+
+    def _pos(self, crossing, labels):
+        """(index into crossing, is a crossing label) per label"""
+        if len(crossing) == 0:
+            return (numpy.zeros(len(labels), dtype=numpy.int64), numpy.zeros(len(labels), dtype=bool))
+        pos = numpy.searchsorted(crossing, labels)
+        pos[pos >= len(crossing)] = 0
+        return (pos, crossing[pos] == labels)
+
+    def _lookup(self, cr, labels):
+        """ids of the given labels of tile cr as far as known (UNKNOWN for open crossing ones)"""
+        tb = self.tables[cr]
+        off = self.dtype.type(self.offsets[cr])
+        if self.simple:
+            out = labels.astype(self.dtype) + off
+            out[labels == 0] = 0
+            return out
+        (crossing, vals) = self._crossOf(cr)
+        rel = tb.prepare()[0][labels].astype(self.dtype)
+        out = numpy.where(rel > 0, rel + off, self.dtype.type(0))
+        (pos, isCross) = self._pos(crossing, labels)
+        out[isCross] = vals[pos[isCross]]
+        return out
 
     def remoteIds(self, cr, labels):
         """final ids of labels of a tile owned by another rank, from the owner's answers so far;
         what is not known yet is queued in self.requests.  Returns (ids, complete)."""
         labels = numpy.asarray(labels, dtype=numpy.int64)
-        out = numpy.zeros(len(labels), dtype=numpy.uint32)
+        out = numpy.zeros(len(labels), dtype=self.dtype)
         found = numpy.zeros(len(labels), dtype=bool)
         if cr in self.remote:
             (known, vals) = self.remote[cr]
@@ -229,45 +251,53 @@ class LazyResolver(object):
             labels = numpy.concatenate([self.remote[cr][0], labels])
             vals = numpy.concatenate([self.remote[cr][1], vals])
         order = numpy.argsort(labels, kind='stable')
-        self.remote[cr] = (labels[order].astype(numpy.int64), vals[order].astype(numpy.uint32))
+        self.remote[cr] = (labels[order].astype(numpy.int64), vals[order].astype(self.dtype))
 
     def answer(self, cr, labels):
         """what an owner can say about labels of its tile cr right now: (labels, final ids) of
         those that are settled"""
         labels = numpy.asarray(labels, dtype=numpy.int64)
-        self.finalIds(cr, labels)
-        vals = self.luts[cr][labels]
+        vals = self._finalIds(cr, labels)
         settled = vals != self.UNKNOWN
         return (labels[settled], vals[settled])
 
-    def finalIds(self, cr, labels):
-        """final ids of the given local labels of tile cr (int64 array).  Entries whose value
-        hangs on a table that is not here stay unknown (and come back as 0): the tile is noted in
-        self.missing, to be fetched before the next call."""
-        lut = self._lutOf(cr)
-        labels = numpy.asarray(labels, dtype=numpy.int64)
-        out = lut[labels]
+    def _finalIds(self, cr, labels):
+        out = self._lookup(cr, labels)
         unknown = out == self.UNKNOWN
         if unknown.any():
-            self._resolveCrossing(cr, lut, labels[unknown])
-            out = lut[labels]
-        return numpy.where(out == self.UNKNOWN, 0, out).astype(numpy.uint32)
+            self._resolveCrossing(cr, numpy.unique(labels[unknown]))
+            out = self._lookup(cr, labels)
+        return out
 
-    def _resolveCrossing(self, cr, lut, labels):
+    def finalIds(self, cr, labels):
+        """final ids of the given local labels of tile cr (int64 array).  Entries whose value
+        hangs on a table that is not here stay open (and come back as 0); self.misses counts
+        them and self.requests says what to ask the owners for."""
+        out = self._finalIds(cr, numpy.asarray(labels, dtype=numpy.int64))
+        return numpy.where(out == self.UNKNOWN, 0, out).astype(self.dtype)
+
+    def _resolveCrossing(self, cr, labels):
         """A crossing segment takes the vote of the left overlap if it crosses that one (the left
         recode is applied after the top one and overrides it, tiling.py:1107-1121), otherwise the
         vote of the top overlap."""
         from .tiling import _modeByKey
         tb = self.tables[cr]
+        (crossing, vals) = self._crossOf(cr)
         (isLeft, segs, nbr, counts) = tb.pairs()
-        wanted = numpy.zeros(tb.maxId + 1, dtype=bool)
-        wanted[labels] = True
-        keyLeft = (tb.flags & _lib.SEG_KEYLEFT) != 0
-        for (which, pairSide, nb) in ((wanted & ~keyLeft, ~isLeft, (cr[0], cr[1] - 1)),
-                (wanted & keyLeft, isLeft, (cr[0] - 1, cr[1]))):
-            sel = pairSide & which[segs]
+        if cr not in self.scratch:
+            self.scratch[cr] = numpy.zeros(tb.maxId + 1, dtype=bool)
+        mark = self.scratch[cr]
+        keyLeft = (tb.flags[labels] & _lib.SEG_KEYLEFT) != 0
+        for (sub, pairSide, nb) in ((labels[~keyLeft], ~isLeft, (cr[0], cr[1] - 1)),
+                (labels[keyLeft], isLeft, (cr[0] - 1, cr[1]))):
+            if len(sub) == 0:
+                continue
+            subPos = self._pos(crossing, sub)[0]
+            mark[sub] = True
+            sel = pairSide & mark[segs]
+            mark[sub] = False
             if not sel.any():
-                lut[which] = 0
+                vals[subPos] = 0
                 continue
             if nb not in self.tables:
                 # a tile of another rank: its owner answers (entries stay open until then)
@@ -275,32 +305,52 @@ class LazyResolver(object):
                 if not complete:
                     self.misses += 1
                     continue
-                mapped = mapped.astype(numpy.int64)
             else:
                 before = self.misses
-                mapped = self.finalIds(nb, nbr[sel]).astype(numpy.int64)
+                mapped = self.finalIds(nb, nbr[sel])
                 if self.misses > before:
                     continue          # the neighbour's own answer is still open somewhere below
-            lut[which] = 0
-            (k, mode) = _modeByKey(segs[sel], mapped, counts[sel])
-            lut[k] = mode.astype(numpy.uint32)
+            vals[subPos] = 0
+            if self.dtype.itemsize > 4:
+                # symbolic ids do not fit the 32 bits _modeByKey packs: vote on their ranks in
+                # ascending order (ties go to the smallest id either way)
+                (uniq, inv) = numpy.unique(mapped, return_inverse=True)
+                (k, mode) = _modeByKey(segs[sel], inv.astype(numpy.int64), counts[sel])
+                vals[self._pos(crossing, k)[0]] = uniq[mode]
+            else:
+                (k, mode) = _modeByKey(segs[sel], mapped.astype(numpy.int64), counts[sel])
+                vals[self._pos(crossing, k)[0]] = mode.astype(self.dtype)
 
     def settle(self, cr):
         """work on every open entry of own tile cr; True when none is left open"""
-        lut = self._lutOf(cr)
         if self.simple:
             return True
-        crossing = self.tables[cr].prepare()[2]
-        unknown = crossing[lut[crossing] == self.UNKNOWN]
+        (crossing, vals) = self._crossOf(cr)
+        unknown = crossing[vals == self.UNKNOWN]
         if len(unknown) > 0:
-            self._resolveCrossing(cr, lut, unknown)
-            return not (lut[unknown] == self.UNKNOWN).any()
+            self._resolveCrossing(cr, unknown)
+            return not (vals == self.UNKNOWN).any()
         return True
 
+    def crossingIds(self, cr):
+        """(labels of the crossing segments of tile cr, their ids; open ones as 0)"""
+        (crossing, vals) = self._crossOf(cr)
+        return (crossing, numpy.where(vals == self.UNKNOWN, 0, vals).astype(self.dtype))
+
     def fullLut(self, cr):
+        """the whole lut of tile cr (an array over its labels)"""
         self.settle(cr)
-        lut = self._lutOf(cr)
-        return numpy.where(lut == self.UNKNOWN, 0, lut).astype(numpy.uint32)
+        tb = self.tables[cr]
+        off = self.dtype.type(self.offsets[cr])
+        if self.simple:
+            lut = numpy.arange(tb.maxId + 1, dtype=self.dtype) + off
+            lut[0] = 0
+            return lut
+        (rel, isNumbered, crossing) = tb.prepare()
+        lut = rel.astype(self.dtype) + isNumbered.astype(self.dtype) * off
+        (cl, cv) = self.crossingIds(cr)
+        lut[cl] = cv
+        return lut
 
 
 def sequentialResolve(order, tables, simple=False):
@@ -389,6 +439,81 @@ class TorchComm(object):
 
     def allgatherArray(self, a, quick=1 << 15):
         """int64 array from every rank -> list of int64 arrays.  One collective when every rank's
+        array fits `quick` entries (slot 0 carries the length), otherwise the sizes first.
+        Staged through pinned host buffers on both sides."""
+        a = numpy.ascontiguousarray(a, dtype=numpy.int64)
+        torch = self.torch
+        if not hasattr(self, '_quickBufs') or self._quickBufs[0].numel() != quick + 1:
+            pin = self.device.type == 'cuda'
+            self._quickBufs = (torch.zeros(quick + 1, dtype=torch.int64, device=self.device),
+                torch.zeros(self.world * (quick + 1), dtype=torch.int64, device=self.device),
+                torch.zeros(quick + 1, dtype=torch.int64, pin_memory=pin),
+                torch.zeros(self.world * (quick + 1), dtype=torch.int64, pin_memory=pin))
+        (mine, everyone, hostMine, hostAll) = self._quickBufs
+        host = hostMine.numpy()
+        host[0] = len(a)
+        if len(a) <= quick:
+            host[1:1 + len(a)] = a
+        mine.copy_(hostMine, non_blocking=True)
+        self.dist.all_gather_into_tensor(everyone, mine)
+        hostAll.copy_(everyone, non_blocking=True)
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream(self.device).synchronize()
+        got = hostAll.numpy().reshape(self.world, quick + 1)
+        sizes = got[:, 0]
+        if (sizes <= quick).all():
+            return [got[r, 1:1 + int(sizes[r])].copy() for r in range(self.world)]
+        return [b.view(numpy.int64) for b in self.allgatherBytes(a.view(numpy.uint8))]
+
+    def exchange(self, sends, recvs):
+        """sends: [(dstRank, tensor)], recvs: [(srcRank, tensor)] in matching order per rank pair"""
+        assert not sends and not recvs
+
+    def allreduceSum(self, array):
+        return array
+
+
+class TorchComm(object):
+    """torch.distributed process group (nccl on the GPUs, gloo in the CPU tests)"""
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.device = device if device is not None else torch.device('cpu')
+
+    def _t(self, a):
+        return self.torch.from_numpy(numpy.ascontiguousarray(a)).to(self.device)
+
+    def allgatherInts(self, values):
+        n = self._t(numpy.array([len(values)], dtype=numpy.int64))
+        sizes = [self.torch.zeros_like(n) for _ in range(self.world)]
+        self.dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(sizes) if sizes else 0
+        mine = numpy.zeros(max(m, 1), dtype=numpy.int64)
+        mine[:len(values)] = values
+        mine = self._t(mine)
+        out = [self.torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine)
+        return [o.cpu().numpy()[:sizes[i]].tolist() for (i, o) in enumerate(out)]
+
+    def allgatherBytes(self, b):
+        if not isinstance(b, numpy.ndarray):
+            b = numpy.frombuffer(b, dtype=numpy.uint8)
+        sizes = [s[0] for s in self.allgatherInts([len(b)])]
+        m = max(max(sizes), 1)
+        mine = numpy.zeros(m, dtype=numpy.uint8)
+        mine[:len(b)] = b
+        mine = self._t(mine)
+        out = [self.torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine)
+        return [o.cpu().numpy()[:sizes[i]] for (i, o) in enumerate(out)]
+
+    def allgatherArray(self, a, quick=1 << 13):
+        """int64 array from every rank -> list of int64 arrays.  One collective when every rank's
         array fits `quick` entries (slot 0 carries the length), otherwise the sizes first."""
         a = numpy.ascontiguousarray(a, dtype=numpy.int64)
         torch = self.torch
@@ -451,6 +576,9 @@ class ShardedStitch(object):
         self.mine = [cr for cr in self.order if self.owner[cr] == comm.rank]
         self.usedFallback = False
         self.forceSequential = False    # (tests) take the fall-back even if the check passes
+        self.earlyTables = {}
+        symbolic = dict((cr, i << self.SHIFT) for (i, cr) in enumerate(self.order))
+        self.resolver = LazyResolver({}, symbolic, simple, dtype=numpy.uint64)
 
     def neighbours(self, cr):
         (c, r) = cr
@@ -484,20 +612,49 @@ class ShardedStitch(object):
         import contextlib
         return self.timings.interval(name) if self.timings is not None else contextlib.nullcontext()
 
+    def early(self, cr, table):
+        """A table of an own tile that exists before run() (the caller computed it while other
+        tiles were still being segmented): its lut is worked out as far as the tables at hand
+        allow -- with symbolic offsets nothing has to wait for the other ranks' counts."""
+        self.earlyTables[cr] = table
+        self.resolver.tables[cr] = table
+        table.prepare()
+        if not self.simple:
+            (up, left) = self.neighbours(cr)
+            if all(nb is None or nb in self.resolver.tables for nb in (up, left)):
+                self.resolver.requests = {}
+                self.resolver.settle(cr)
+
     def run(self, ops):
         """returns (maxSegId, offsets of all tiles, luts of own tiles)"""
         with self._timed('stitch_strips'):
             received = self._exchangeStrips(ops)
         with self._timed('stitch_owntables'):
             tables = self._ownTables(ops, received)
-        with self._timed('stitch_offsets'):
-            (steps, offsets, maxSegId) = self._offsets(tables)
         with self._timed('stitch_resolve'):
-            (luts, offsets, maxSegId) = self._resolve(tables, steps, offsets, maxSegId)
+            (final, luts, offsets, maxSegId) = self._resolve(tables)
         with self._timed('stitch_apply'):
             for cr in self.mine:
-                ops.apply(cr, luts[cr], tables[cr])
+                if cr in luts:
+                    ops.apply(cr, luts[cr], tables[cr])
+                elif hasattr(ops, 'applyRel'):
+                    # offset + rank for the tile's own segments is left to the device; the host
+                    # only hands over the ids of the crossing segments
+                    ops.applyRel(cr, offsets[cr], final[cr][0], final[cr][1], tables[cr])
+                else:
+                    luts[cr] = self._fullLut(tables[cr], offsets[cr], final[cr])
+                    ops.apply(cr, luts[cr], tables[cr])
         return (maxSegId, offsets, luts)
+
+    def _fullLut(self, tb, offset, crossFinal):
+        if self.simple:
+            lut = numpy.arange(tb.maxId + 1, dtype=numpy.uint32) + numpy.uint32(offset)
+            lut[0] = 0
+            return lut
+        (rel, isNumbered, crossing) = tb.prepare()
+        lut = rel + isNumbered * numpy.uint32(offset)
+        lut[crossFinal[0]] = crossFinal[1]
+        return lut
 
     def _exchangeStrips(self, ops):
         comm = self.comm
@@ -518,6 +675,9 @@ class ShardedStitch(object):
         # 2. tables of own tiles
         tables = {}
         for cr in self.mine:
+            if cr in self.earlyTables:
+                tables[cr] = self.earlyTables[cr]
+                continue
             (up, left) = self.neighbours(cr)
             top = lf = None
             if not self.simple:
@@ -526,90 +686,128 @@ class ShardedStitch(object):
                 if left is not None:
                     lf = 'local' if self.owner[left] == comm.rank else received[(left, 'right')]
             tables[cr] = ops.tables(cr, top, lf)
+            self.resolver.tables[cr] = tables[cr]
         return tables
 
-    def _offsets(self, tables):
-        comm = self.comm
-        # 3. offsets.  The reference moves the running maximum on tile after tile:
+    # The id offset of a tile is the sum of one integer per earlier tile, which the other ranks
+    # only know when they are done.  Nothing else in the resolve needs the offsets' VALUES: ids
+    # are handled as (index of the tile that numbered the segment) << 32 | rank, which sort like
+    # the final ids (offsets grow with the tile index) and are equal exactly when those are, and
+    # are turned into offset + rank at the very end.
+    SHIFT = 32
+
+    def _stepOf(self, tb):
+        # The reference moves the running maximum on tile after tile:
         # maxSegId = max(maxSegId, trimmed.max()) (tiling.py:1042-1043).  Inside the trimmed
         # window a tile has its own numbered segments (offset + rank) and segments recoded to ids
         # of EARLIER tiles; unless one of those carries an id above the running maximum (a
         # neighbour's segment that was numbered without having a pixel in its own trimmed
         # window), the maximum moves on by the highest rank present in the window.  Take that as
-        # the hypothesis -- offsets = running sum of one integer per tile, known to every rank
-        # after one all-gather -- resolve, and check the recurrence on every tile afterwards.
-        mineInts = []
-        for cr in self.mine:
-            tb = tables[cr]
-            step = tb.maxLabelInTrim if self.simple else (tb.prepare() and tb.cachedMaxRankInTrim)
-            mineInts += [cr[0], cr[1], step]
-        steps = {}
-        for vals in comm.allgatherArray(numpy.array(mineInts, dtype=numpy.int64)):
-            for i in range(0, len(vals), 3):
-                steps[(int(vals[i]), int(vals[i + 1]))] = int(vals[i + 2])
-        offsets = {}
-        offset = 0
-        for cr in self.order:
-            offsets[cr] = offset
-            offset += steps[cr]
-        maxSegId = offset
-        return (steps, offsets, maxSegId)
+        # the hypothesis -- offsets = running sum of one integer per tile -- and check the
+        # recurrence on every tile afterwards.
+        if self.simple:
+            return tb.maxLabelInTrim
+        tb.prepare()
+        return tb.cachedMaxRankInTrim
 
-    def _resolve(self, tables, steps, offsets, maxSegId):
+    def _translate(self, lut, realOffsets):
+        idx = (lut >> numpy.uint64(self.SHIFT)).astype(numpy.int64)
+        return (realOffsets[idx] + (lut & numpy.uint64((1 << self.SHIFT) - 1))).astype(numpy.uint32)
+
+    def _resolve(self, tables):
         comm = self.comm
-        # 4. final ids of own tiles.  A crossing segment takes the final id of the neighbour
+        resolver = self.resolver
+        index = dict((cr, i) for (i, cr) in enumerate(self.order))
+        # Final ids of own tiles.  A crossing segment takes the final id of the neighbour
         # segment it overlaps most; when that neighbour tile lives on another rank its OWNER is
-        # asked for the final ids of the labels in question (a few thousand per boundary tile),
-        # and answers what it has settled.  An id inherited through several tiles around a
-        # corner takes one more round per hop.
-        luts = {}
-        resolver = LazyResolver(dict(tables), offsets, self.simple)
-        for _round in range(len(self.order) + 3):
+        # asked for the (symbolic) final ids of the labels in question (a few thousand per
+        # boundary tile), and answers what it has settled.  An id inherited through several
+        # tiles around a corner takes one more round per hop.  The first message of a rank also
+        # carries the steps of its tiles, its last one the outcome of its check.
+        steps = {}
+        offsets = None
+        realOffsets = None
+        luts = {}       # whole luts: only after the fall-back
+        final = {}      # own tile -> (labels of its crossing segments, their final ids)
+        ok = None
+        first = True
+        for _round in range(len(self.order) + 4):
             resolver.requests = {}
-            for cr in self.mine:          # (entries settled in an earlier round are kept)
+            for cr in self.mine:          # (entries settled earlier are kept)
                 resolver.settle(cr)
-            req = []
+            msg = []
+            if first:
+                head = [len(self.mine)]
+                for cr in self.mine:
+                    head += [cr[0], cr[1], self._stepOf(tables[cr])]
+                msg.append(numpy.array(head, dtype=numpy.int64))
+            nReq = len(resolver.requests)
+            if nReq == 0 and not first and ok is None:
+                # everything of this rank is settled and the offsets are known: translate and
+                # check the hypothesis
+                ok = 1
+                for cr in self.mine:
+                    tb = tables[cr]
+                    (cl, cv) = resolver.crossingIds(cr)
+                    final[cr] = (cl, self._translate(cv, realOffsets))
+                    if self.simple:
+                        trimmedMax = offsets[cr] + tb.maxLabelInTrim if tb.maxLabelInTrim else 0
+                    else:
+                        trimmedMax = offsets[cr] + tb.cachedMaxRankInTrim if tb.cachedMaxRankInTrim else 0
+                        if tb.crossInTrimMask.any():
+                            trimmedMax = max(trimmedMax, int(final[cr][1][tb.crossInTrimMask].max()))
+                    if max(offsets[cr], trimmedMax) != offsets[cr] + steps[cr] or self.forceSequential:
+                        ok = 0
+            msg.append(numpy.array([nReq, -1 if ok is None else ok], dtype=numpy.int64))
             for (cr, parts) in sorted(resolver.requests.items()):
                 labels = numpy.unique(numpy.concatenate(parts))
-                req += [numpy.array([cr[0], cr[1], len(labels)], dtype=numpy.int64), labels]
-            allReq = comm.allgatherArray(numpy.concatenate(req) if req else numpy.zeros(0, numpy.int64))
-            if not any(len(a) for a in allReq):
-                break
-            ans = []
+                msg += [numpy.array([cr[0], cr[1], len(labels)], dtype=numpy.int64), labels]
+            allReq = comm.allgatherArray(numpy.concatenate(msg))
+            asked = []
+            states = []
             for a in allReq:
                 o = 0
-                while o < len(a):
-                    (c, r, n) = (int(v) for v in a[o:o + 3])
-                    labels = a[o + 3:o + 3 + n]
-                    o += 3 + n
-                    if self.owner[(c, r)] == comm.rank:
-                        (lab, vals) = resolver.answer((c, r), labels)
-                        ans += [numpy.array([c, r, len(lab)], dtype=numpy.int64), lab, vals.astype(numpy.int64)]
+                if first:
+                    n = int(a[0])
+                    for i in range(n):
+                        steps[(int(a[1 + 3 * i]), int(a[2 + 3 * i]))] = int(a[3 + 3 * i])
+                    o = 1 + 3 * n
+                (n, state) = (int(a[o]), int(a[o + 1]))
+                o += 2
+                states.append(state)
+                for _ in range(n):
+                    (c, r, m) = (int(v) for v in a[o:o + 3])
+                    asked.append(((c, r), a[o + 3:o + 3 + m]))
+                    o += 3 + m
+            if first:
+                first = False
+                offsets = {}
+                realOffsets = numpy.zeros(len(self.order) + 1, dtype=numpy.uint64)
+                offset = 0
+                for (i, cr) in enumerate(self.order):
+                    offsets[cr] = offset
+                    realOffsets[i] = offset
+                    offset += steps[cr]
+                maxSegId = offset
+            if not asked:
+                if all(st >= 0 for st in states):
+                    break
+                continue          # (someone settled in this round and reports its check next)
+            ans = []
+            for (cr, labels) in asked:
+                if self.owner[cr] == comm.rank:
+                    (lab, vals) = resolver.answer(cr, labels)
+                    ans += [numpy.array([cr[0], cr[1], len(lab)], dtype=numpy.int64), lab, vals.astype(numpy.int64)]
             for a in comm.allgatherArray(numpy.concatenate(ans) if ans else numpy.zeros(0, numpy.int64)):
                 o = 0
                 while o < len(a):
                     (c, r, n) = (int(v) for v in a[o:o + 3])
                     if (c, r) in resolver.requests:
-                        resolver.addRemote((c, r), a[o + 3:o + 3 + n], a[o + 3 + n:o + 3 + 2 * n])
+                        resolver.addRemote((c, r), a[o + 3:o + 3 + n], a[o + 3 + n:o + 3 + 2 * n].astype(numpy.uint64))
                     o += 3 + 2 * n
         else:
             raise RuntimeError('sharded stitch: look-ups across ranks did not settle')
-        for cr in self.mine:
-            luts[cr] = resolver.luts[cr]          # nothing is open any more
-        # the check of the hypothesis
-        ok = 1
-        for cr in self.mine:
-            tb = tables[cr]
-            if self.simple:
-                trimmedMax = offsets[cr] + tb.maxLabelInTrim if tb.maxLabelInTrim else 0
-            else:
-                tb.prepare()
-                trimmedMax = offsets[cr] + tb.cachedMaxRankInTrim if tb.cachedMaxRankInTrim else 0
-                if len(tb.crossingInTrim):
-                    trimmedMax = max(trimmedMax, int(luts[cr][tb.crossingInTrim].max()))
-            if max(offsets[cr], trimmedMax) != offsets[cr] + steps[cr] or self.forceSequential:
-                ok = 0
-        if min(int(v[0]) for v in comm.allgatherArray(numpy.array([ok], dtype=numpy.int64))) == 0:
+        if min(states) == 0:
             # some window holds an inherited id above the running maximum: replay the
             # reference's sequential order over all tables, on every rank
             self.usedFallback = True
@@ -619,4 +817,4 @@ class ShardedStitch(object):
             (allLuts, offsets, maxSegId) = sequentialResolve(self.order, known, self.simple)
             luts = dict((cr, allLuts[cr]) for cr in self.mine)
 
-        return (luts, offsets, maxSegId)
+        return (final, luts, offsets, maxSegId)

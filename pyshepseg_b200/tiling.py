@@ -739,12 +739,28 @@ class TiledSegmenter(object):
         from . import distributed
         return distributed.TileTable(tables.maxId, tables.countNew, rank, flags, pairKeys, pairCounts)
 
-    def applyLut(self, slot, tile, lut, maxId, sink, hist, histLen, deferred=None, fetchLen=0):
+    def applyLut(self, slot, tile, lut, maxId, sink, hist, histLen, deferred=None, fetchLen=0, rel=None):
         """Device phase 2: final ids over the trimmed window, on the device, then to the sink.
         deferred (a list, for the last tile of a run): if the window can travel on its own, the
         histogram copy is queued BEFORE it (mark 0), the window copy is left in flight (mark 1)
-        and 'window' is appended to the list: the caller works on the histogram meanwhile."""
+        and 'window' is appended to the list: the caller works on the histogram meanwhile.
+        rel = (rel, offset, crossLabels, crossIds) instead of lut: the lut is put together on
+        the device (ssg_apply_rel_lut_device)."""
         ctx = slot.ctx
+
+        def kernel(out, outStride):
+            if rel is None:
+                ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
+                    int(maxId), top, bottom, left, right, out, outStride, hist.dev, hist.cap)
+                self.h2dBytes += lut.nbytes
+            else:
+                (relArr, offset, crossLabels, crossIds) = rel
+                ctx.call('ssg_apply_rel_lut_device', tile.buf[1], tile.ysize, tile.xsize,
+                    None if relArr is None else _lib.ptr(relArr), int(maxId), int(offset), len(crossLabels),
+                    _lib.ptr(crossLabels) if len(crossLabels) else None,
+                    _lib.ptr(crossIds) if len(crossLabels) else None,
+                    top, bottom, left, right, out, outStride, hist.dev, hist.cap)
+                self.h2dBytes += (0 if relArr is None else relArr.nbytes) + 8 * len(crossLabels)
         (top, bottom, left, right) = tileMargins(self.tileInfo, tile.col, tile.row, tile.xsize,
             tile.ysize, self.overlapSize)
         (wr, wc) = (bottom - top, right - left)
@@ -753,13 +769,10 @@ class TiledSegmenter(object):
         yout = tile.ypos + top - getattr(sink, 'yoff', 0)
         if isinstance(sink, DeviceMosaicSink):
             # the mosaic lives in HBM: write the window in place
-            ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
-                int(maxId), top, bottom, left, right,
-                sink.devPtr + (yout * sink.xsize + xout) * 4, sink.xsize, hist.dev, hist.cap)
+            kernel(sink.devPtr + (yout * sink.xsize + xout) * 4, sink.xsize)
         else:
             (window, winDev) = slot.windowFor(wr * wc)
-            ctx.call('ssg_apply_lut_device', tile.buf[1], tile.ysize, tile.xsize, _lib.ptr(lut),
-                int(maxId), top, bottom, left, right, winDev, wc, hist.dev, hist.cap)
+            kernel(winDev, wc)
             arr = getattr(sink, 'array', None)
             if (type(sink) is rasterfile.MemorySink and isinstance(arr, numpy.ndarray) and
                     arr.flags.c_contiguous and arr.dtype == numpy.uint32):
@@ -780,7 +793,6 @@ class TiledSegmenter(object):
                 sink.write(out, xout, yout)
                 sink.writeOverviews(out, xout, yout)
             self.d2hBytes += wr * wc * 4
-        self.h2dBytes += lut.nbytes
 
     def stitchOne(self, slot, pool, tile, offset, sink, hist, deferred=None):
         self.mark('tile %d,%d stitch start' % (tile.col, tile.row))
@@ -940,7 +952,6 @@ class TiledSegmenter(object):
         stripDev = cudaDev if onDevice else torch.device('cpu')
         seg = self
         keep = []     # device copies of strips received through the host
-        early = {}    # tables computed while the other tiles were still being segmented
 
         class Ops(object):
             def sendStrip(self, cr, which):
@@ -970,8 +981,6 @@ class TiledSegmenter(object):
                 return d
 
             def tables(self, cr, top, left):
-                if cr in early:
-                    return early.pop(cr)
                 t = seg.tiles[cr]
                 (topB, topStride, leftB, leftStride) = (None, 0, None, 0)
                 if top is not None:
@@ -994,6 +1003,16 @@ class TiledSegmenter(object):
                 t = seg.tiles[cr]
                 t.lut = lut
                 seg.applyLut(main, t, lut, tb.maxId, sink, hist, int(lut.max()) + 1 if len(lut) else 1)
+
+            def applyRel(self, cr, offset, crossLabels, crossIds, tb):
+                t = seg.tiles[cr]
+                top = offset + (tb.maxId if seg.simple else tb.countNew)
+                if len(crossIds):
+                    top = max(top, int(crossIds.max()))
+                seg.applyLut(main, t, None, tb.maxId, sink, hist, top + 1, rel=(
+                    None if seg.simple else tb.prepare()[0], offset,
+                    numpy.ascontiguousarray(crossLabels, dtype=numpy.uint32),
+                    numpy.ascontiguousarray(crossIds, dtype=numpy.uint32)))
 
         main.lock.acquire()
         before = main.ctx.launch_count()
@@ -1029,9 +1048,9 @@ class TiledSegmenter(object):
                     # done: they come earlier in the order) gets its tables while the workers go on
                     (up, left) = stitch.neighbours(cr)
                     if all(nb is None or stitch.owner[nb] == comm.rank for nb in (up, left)):
-                        early[cr] = ops.tables(cr, None if (up is None or self.simple) else 'local',
-                            None if (left is None or self.simple) else 'local')
-                        early[cr].prepare()      # the offset-independent part of its lut, too
+                        # (and its lut, as far as it hangs on own tiles only)
+                        stitch.early(cr, ops.tables(cr, None if (up is None or self.simple) else 'local',
+                            None if (left is None or self.simple) else 'local'))
                 for th in workers:
                     th.join()
             with self.timings.interval('stitchtiles'):
@@ -1052,8 +1071,14 @@ class TiledSegmenter(object):
                         main.ctx.synchronize()
                         torch.distributed.reduce(t, 0)
                         if comm.rank == 0:
-                            histogram = t.cpu().numpy().astype(numpy.float64)
-                            histogram[0] = 0
+                            # converted on the device, copied into pinned memory (the caching
+                            # host allocator hands the same block out again run after run)
+                            f = t.to(torch.float64)
+                            f[0] = 0
+                            h = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                            h.copy_(f, non_blocking=True)
+                            torch.cuda.current_stream(cudaDev).synchronize()
+                            histogram = h.numpy()
                         else:
                             histogram = numpy.zeros(0)
                     else:
