@@ -358,7 +358,7 @@ def run_reference(args, wl):
     img = make_scene(wl, seed=1)
     centres = scene_centres(wl, img)
     from pyshepseg_b200 import tiling
-    (gr, gc) = SCENE_GRID.get(args.gpus, (1, args.gpus))
+    (gr, gc) = (1, 1) if wl.get('strong') else SCENE_GRID.get(args.gpus, (1, args.gpus))
     tileInfo = tiling.getTilesForFile((wl['cols'] * gc, wl['rows'] * gr), wl['tileSize'], wl['overlapSize'])
     ratio = tile_pixel_ratio(tileInfo, wl['rows'] * gr, wl['cols'] * gc)
     haveRef = os.path.isdir(os.path.join(REF_DIR, 'pyshepseg')) and os.path.exists(scene_path(wl)) \
@@ -409,17 +409,18 @@ def run_reference(args, wl):
 
 
 def workload_config(wl, gpus, shape=None, tileInfo=None):
-    (gr, gc) = SCENE_GRID.get(gpus, (1, gpus))
+    (gr, gc) = (1, 1) if wl.get('strong') else SCENE_GRID.get(gpus, (1, gpus))
     (nR, nC) = shape if shape is not None else (wl['rows'] * gr, wl['cols'] * gc)
-    name = wl['name'] if gpus == 1 else '%s_mosaic_of_%dx%d_scenes' % (wl['name'], gr, gc)
+    name = wl['name'] if (gpus == 1 or wl.get('strong')) else '%s_mosaic_of_%dx%d_scenes' % (wl['name'], gr, gc)
     tiles = ('%dx%d' % (tileInfo.nrows, tileInfo.ncols)) if tileInfo is not None else None
     return {'workload': name, 'raster': [wl['bands'], nR, nC], 'dtype': 'uint16',
         'tileSize': wl['tileSize'], 'overlapSize': wl['overlapSize'], 'tiles': tiles,
         'numClusters': wl['numClusters'], 'minSegmentSize': wl['minSegmentSize'],
         'maxSpectralDiff': wl['maxSpectralDiff'], 'fourConnected': wl['fourConnected'],
-        'scenes': gpus,
-        'parallelism': ('one mosaic of %d scenes, tiles dealt over %d GPUs in row-major chunks, overlap '
-            'strips over NCCL, ids global' % (gpus, gpus)) if gpus > 1 else 'single GPU',
+        'scenes': 1 if wl.get('strong') else gpus,
+        'parallelism': (('one mosaic, the same for every N, ' if wl.get('strong') else 'one mosaic of %d scenes, ' % gpus) +
+            'tiles dealt over %d GPUs in row-major chunks, overlap strips over NCCL, ids global' % gpus)
+            if gpus > 1 else 'single GPU',
         'l2_policy': 'inputs larger than L2 (964 MB raster, 482 MB mosaic per scene)'}
 
 
@@ -450,22 +451,24 @@ def run_ours(args, wl):
     # N = 1: the scene.  N > 1: ONE mosaic of N scenes (weak scaling), its tiles dealt over the
     # ranks in contiguous row-major chunks; a rank holds the row band its tiles cover.
     nB = wl['bands']
-    (gr, gc) = SCENE_GRID.get(world, (1, world))
+    (gr, gc) = (1, 1) if wl.get('strong') else SCENE_GRID.get(world, (1, world))
     (nR, nC) = (wl['rows'] * gr, wl['cols'] * gc)
     tileInfo = tiling.getTilesForFile((nC, nR), wl['tileSize'], wl['overlapSize'])
     comm = None
     (y0, y1) = (0, nR)
+    (x0, x1) = (0, nC)
     if world > 1:
         comm = distributed.TorchComm(torch.device('cuda', local))
         owner = distributed.partitionTiles(tileInfo, world)
         mineT = [tileInfo.tiles[cr] for cr in tileInfo.tiles if owner[cr] == rank]
         (y0, y1) = (min(t[1] for t in mineT), max(t[1] + t[3] for t in mineT))
-    bandRows = y1 - y0
-    pinnedImg = _lib.PinnedArray((nB, bandRows, nC), numpy.uint16)
+        (x0, x1) = (min(t[0] for t in mineT), max(t[0] + t[2] for t in mineT))
+    (bandRows, bandCols) = (y1 - y0, x1 - x0)      # the window of the raster this rank's tiles cover
+    pinnedImg = _lib.PinnedArray((nB, bandRows, bandCols), numpy.uint16)
     if world == 1:
         img = make_scene(wl, seed=1, out=pinnedImg.array)
     else:
-        img = synth.synth_window(nR, nC, nB, 1, y0, 0, bandRows, nC, out=pinnedImg.array)
+        img = synth.synth_window(nR, nC, nB, 1, y0, x0, bandRows, bandCols, out=pinnedImg.array)
     if rank == 0:
         centres = scene_centres(wl, img)
     else:
@@ -478,23 +481,23 @@ def run_ours(args, wl):
     km = KM(centres)
     msd = shepseg.autoMaxSpectralDiff(km, wl['maxSpectralDiff'], 50)
     thr = shepseg.spectralThreshold(msd)
-    pinnedOut = _lib.PinnedArray((bandRows, nC), numpy.uint32)
+    pinnedOut = _lib.PinnedArray((bandRows, bandCols), numpy.uint32)
 
     state = tiling.gpuState(local)
     ctx0 = state.slot(0).ctx
     devImg = ctx0.dev_alloc(img.nbytes)
     ctx0.call('ssg_memcpy_h2d', devImg, _lib.ptr(img), img.nbytes)
     ctx0.synchronize()
-    devMosaic = ctx0.dev_alloc(bandRows * nC * 4)
+    devMosaic = ctx0.dev_alloc(bandRows * bandCols * 4)
 
     def step_resident(profile=False):
         cfg = tiling.SegmentationConcurrencyConfig(devices=[local]) if (RESIDENT_WORKERS == 0 or profile) else \
             tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=RESIDENT_WORKERS,
                 devices=[local], tileCompletionTimeout=600)
-        seg = tiling.TiledSegmenter(tiling.DeviceRaster(devImg, nB, bandRows, nC, numpy.uint16, yoff=y0),
+        seg = tiling.TiledSegmenter(tiling.DeviceRaster(devImg, nB, bandRows, bandCols, numpy.uint16, yoff=y0, xoff=x0),
             range(1, nB + 1), tileInfo, wl['overlapSize'], centres, None, wl['fourConnected'],
             wl['minSegmentSize'], thr, False, cfg, timinghooks.Timers(), profile=profile)
-        (maxSegId, hist) = seg.run(tiling.DeviceMosaicSink(devMosaic, nC, bandRows, yoff=y0), comm)
+        (maxSegId, hist) = seg.run(tiling.DeviceMosaicSink(devMosaic, bandCols, bandRows, yoff=y0, xoff=x0), comm)
         return (seg, maxSegId)
 
     def step_e2e():
@@ -503,8 +506,8 @@ def run_ours(args, wl):
         cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=E2E_WORKERS,
             devices=[local], tileCompletionTimeout=600)
         cfg.comm = comm
-        sink = rasterfile.MemorySink(nC, bandRows, array=pinnedOut.array, yoff=y0)
-        src = rasterfile.MemoryRaster(img, yoff=y0, fullYsize=nR)
+        sink = rasterfile.MemorySink(bandCols, bandRows, array=pinnedOut.array, yoff=y0, xoff=x0)
+        src = rasterfile.MemoryRaster(img, yoff=y0, fullYsize=nR, xoff=x0, fullXsize=nC)
         res = tiling.doTiledShepherdSegmentation(src, sink, tileSize=wl['tileSize'], overlapSize=wl['overlapSize'],
             minSegmentSize=wl['minSegmentSize'], numClusters=wl['numClusters'], maxSpectralDiff=wl['maxSpectralDiff'],
             fourConnected=wl['fourConnected'], kmeansObj=km, concurrencyCfg=cfg, returnGDALDS=True)
@@ -591,9 +594,10 @@ def run_ours(args, wl):
 
     # the e2e mosaic must be the resident mosaic (same labels, one went over PCIe)
     midRow = bandRows // 2
-    check = numpy.empty((64, nC), dtype=numpy.uint32)
-    ctx0.call('ssg_memcpy_d2h', _lib.ptr(check), devMosaic + midRow * nC * 4, check.nbytes)
-    sameMosaic = bool(numpy.array_equal(check, pinnedOut.array[midRow:midRow + 64]))
+    check = numpy.empty((64, bandCols), dtype=numpy.uint32)
+    ctx0.call('ssg_memcpy_d2h', _lib.ptr(check), devMosaic + midRow * bandCols * 4, check.nbytes)
+    edge = wl['overlapSize'] if dist is not None else 0     # (the rim of a rank's window belongs to its neighbours)
+    sameMosaic = bool(numpy.array_equal(check[:, edge:bandCols - edge], pinnedOut.array[midRow:midRow + 64, edge:bandCols - edge]))
     if dist is not None:
         t = torch.tensor([int(sameMosaic)], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -605,16 +609,17 @@ def run_ours(args, wl):
     if dist is not None and not args.no_parity:
         import zlib
         bounds = [None] * world
-        dist.all_gather_object(bounds, (y0, y1))
+        dist.all_gather_object(bounds, (y0, y1, x0, x1))
         bandT = torch.from_numpy(img.view(numpy.int16)).cuda()
         full = None
         if rank == 0:
             full = torch.empty((nB, nR, nC), dtype=torch.int16, device='cuda')
-            full[:, y0:y1] = bandT
+            full[:, y0:y1, x0:x1] = bandT
             for r in range(1, world):
-                tmp = torch.empty((nB, bounds[r][1] - bounds[r][0], nC), dtype=torch.int16, device='cuda')
+                (ry0, ry1, rx0, rx1) = bounds[r]
+                tmp = torch.empty((nB, ry1 - ry0, rx1 - rx0), dtype=torch.int16, device='cuda')
                 dist.recv(tmp.view(torch.uint8), r)      # (NCCL has no 16-bit integer type)
-                full[:, bounds[r][0]:bounds[r][1]] = tmp
+                full[:, ry0:ry1, rx0:rx1] = tmp
                 del tmp
         else:
             dist.send(bandT.view(torch.uint8), 0)
@@ -624,7 +629,7 @@ def run_ours(args, wl):
             if owner[cr] != rank:
                 continue
             (top, bottom, left, right) = tiling.tileMargins(tileInfo, cr[0], cr[1], xs, ys, wl['overlapSize'])
-            win = pinnedOut.array[y + top - y0:y + bottom - y0, x + left:x + right]
+            win = pinnedOut.array[y + top - y0:y + bottom - y0, x + left - x0:x + right - x0]
             part[y + top:y + bottom, x + left:x + right] = torch.from_numpy(
                 numpy.ascontiguousarray(win).view(numpy.int32)).cuda()
         dist.reduce(part, 0)
@@ -753,7 +758,7 @@ def run_ours(args, wl):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': msResident / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u16', 'data': 'synthetic',
+            'scaling': 'strong' if wl.get('strong') else 'weak', 'vs_baseline': None, 'dtype': 'u16', 'data': 'synthetic',
             'config': workload_config(wl, args.gpus, (nR, nC), tileInfo),
             'e2e': {'value': e2eValue, 'unit': UNIT, 'ms_per_step': msE2E / args.steps,
                 'h2d_bytes_per_step': h2dBytes, 'd2h_bytes_per_step': d2hBytes,
@@ -796,10 +801,17 @@ def main():
     ap.add_argument('--no-parity', action='store_true', help='skip the oracle check of the benched mosaic')
     ap.add_argument('--port-only', action='store_true', help='reference arm: time the C port even if baseline/_ref exists')
     ap.add_argument('--verbose-steps', action='store_true', help='print every timed step (stderr)')
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c4_40000'],
+        help='c2: the 10980x10980x4 scene (N > 1: a mosaic of N scenes, weak scaling); c4_40000: BASELINE '
+             'config 4, one 40000x40000x4 mosaic for every N (strong scaling)')
     args = ap.parse_args()
     wl = dict(WORKLOAD)
     if args.quick:
         wl.update({'name': 'quick_2700x2700x4', 'rows': 2700, 'cols': 2700, 'tileSize': 1024, 'overlapSize': 256})
+    if args.workload == 'c4_40000':
+        wl.update({'name': 'mosaic_40000x40000x4_u16_tiled', 'rows': 40000, 'cols': 40000, 'strong': True})
+        if args.quick:
+            wl.update({'name': 'quick_mosaic_6000x6000x4', 'rows': 6000, 'cols': 6000})
     if args.impl == 'reference':
         run_reference(args, wl)
     else:

@@ -241,7 +241,7 @@ typedef struct ssg_tile_tables {
     uint32_t maxId;     /* largest label in the tile */
     uint32_t countNew;  /* segments numbered by this tile (flag SSG_SEG_NUMBERED) */
     uint32_t numPairs;  /* distinct (strip, segment, neighbour label) triples */
-    uint32_t reserved;
+    uint32_t maxRankInTrim; /* highest rank among the numbered segments with a pixel in the trimmed window */
 } ssg_tile_tables;
 
 #define SSG_SEG_PRESENT 1u   /* id owns at least one pixel of the tile */
@@ -278,13 +278,15 @@ int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, i
                          const uint32_t *lutHost, uint32_t maxId, int64_t top, int64_t bottom,
                          int64_t left, int64_t right, uint32_t *outDev, int64_t outStride,
                          uint64_t *histDev, int64_t histLen);
-/* The same with the lut put together on the device: lut[i] = offset + relHost[i] where
- * relHost[i] != 0 (the rank of a segment the tile numbered itself, tiling.py:1264-1267;
- * relHost NULL: every label numbers itself, the simple recode of tiling.py:1067-1092), then
+/* The same with the lut put together on the device: lut[i] = offset + rankHost[i] where
+ * flagsHost[i] has SSG_SEG_NUMBERED (a segment the tile numbered itself, tiling.py:1264-1267;
+ * both as ssg_tile_tables_fetch returned them; rankHost NULL: every label numbers itself, the
+ * simple recode of tiling.py:1067-1092), 0 elsewhere, then
  * lut[crossLabelsHost[j]] = crossIdsHost[j] for the nCross segments that take a neighbour's id.
  * Used when the offset is the last thing to become known (tiles sharded over several GPUs). */
 int ssg_apply_rel_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
-                             const uint32_t *relHost, uint32_t maxId, uint32_t offset, int64_t nCross,
+                             const uint32_t *rankHost, const uint8_t *flagsHost, uint32_t maxId,
+                             uint32_t offset, int64_t nCross,
                              const uint32_t *crossLabelsHost, const uint32_t *crossIdsHost,
                              int64_t top, int64_t bottom, int64_t left, int64_t right,
                              uint32_t *outDev, int64_t outStride, uint64_t *histDev, int64_t histLen);

@@ -58,7 +58,7 @@ class TileResult(ctypes.Structure):
 
 class TileTables(ctypes.Structure):
     _fields_ = [('maxId', ctypes.c_uint32), ('countNew', ctypes.c_uint32),
-        ('numPairs', ctypes.c_uint32), ('reserved', ctypes.c_uint32)]
+        ('numPairs', ctypes.c_uint32), ('maxRankInTrim', ctypes.c_uint32)]
 
 
 _c = ctypes
@@ -96,7 +96,7 @@ SIGNATURES = {
     'ssg_tile_tables_fetch': (_i, [_vp, _vp, _vp, _vp, _vp]),
     'ssg_apply_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _u32, _i64, _i64, _i64, _i64, _vp, _i64,
         _vp, _i64]),
-    'ssg_apply_rel_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _u32, _u32, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
+    'ssg_apply_rel_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _u32, _u32, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
         _vp, _i64, _vp, _i64]),
     'ssg_dev_alloc': (_i, [_vp, _sz, _c.POINTER(_vp)]),
     'ssg_dev_free': (_i, [_vp, _vp]),

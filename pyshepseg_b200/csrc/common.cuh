@@ -110,6 +110,7 @@ enum Counter {
     C_SCRATCH1,
     C_SCRATCH2,
     C_SCRATCH3,
+    C_MAXRANKTRIM,     // stitch: highest rank of a self-numbered segment inside the trimmed window
     C_COUNT = 32
 };
 

@@ -159,13 +159,21 @@ k_tile_flags(StitchTables tb, int64_t len, int hasTop, int hasLeft, unsigned cha
 }
 
 __global__ void __launch_bounds__(256)
-k_tile_ranks(const unsigned *__restrict__ numbered, const unsigned *__restrict__ excl, int64_t len,
-             unsigned *rank, unsigned long long *counters)
+k_tile_ranks(const unsigned *__restrict__ numbered, const unsigned *__restrict__ excl,
+             const unsigned char *__restrict__ flags, int64_t len, unsigned *rank, unsigned long long *counters)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= len) return;
-    rank[s] = numbered[s] ? excl[s] + 1u : 0u;
-    if (s == len - 1) counters[C_SCRATCH1] = (unsigned long long)excl[s] + numbered[s];
+    unsigned inTrim = 0;
+    if (s < len) {
+        const unsigned r = numbered[s] ? excl[s] + 1u : 0u;
+        rank[s] = r;
+        if (s == len - 1) counters[C_SCRATCH1] = (unsigned long long)excl[s] + numbered[s];
+        if (flags[s] & SSG_SEG_INTRIM) inTrim = r;
+    }
+    // the highest rank among the numbered segments with a pixel in the trimmed window: by how
+    // much the tile moves the running maximum on (tiling.py:1042-1043)
+    inTrim = __reduce_max_sync(0xffffffffu, inTrim);
+    if ((threadIdx.x & 31) == 0 && inTrim) atomicMax(counters + C_MAXRANKTRIM, (unsigned long long)inTrim);
 }
 
 // (strip, segment, neighbour label) keys of the strip pixels of the crossing segments
@@ -261,6 +269,7 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
 
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_MAXLABEL, 0, sizeof(unsigned long long), ctx->stream));
     SSG_CUDA(ctx, cudaMemsetAsync(counters + C_SCRATCH1, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SSG_CUDA(ctx, cudaMemsetAsync(counters + C_MAXRANKTRIM, 0, sizeof(unsigned long long), ctx->stream));
     unsigned maxId = maxIdHint;
     if (maxId == 0) {       // the caller does not know the largest label: look for it
         SSG_PROF_BEGIN(ctx, "k_tile_max");
@@ -297,7 +306,7 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     SSG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tmpBytes, numbered, excl, (int)len, ctx->stream));
     SSG_LAUNCHED(ctx);
     SSG_PROF_BEGIN(ctx, "k_tile_ranks");
-    k_tile_ranks<<<gridFor(len, 256), 256, 0, ctx->stream>>>(numbered, excl, len, rank, counters);
+    k_tile_ranks<<<gridFor(len, 256), 256, 0, ctx->stream>>>(numbered, excl, flags, len, rank, counters);
     SSG_LAUNCHED(ctx);
 
     // neighbour-label histograms of the crossing segments
@@ -347,6 +356,7 @@ extern "C" int ssg_tile_tables_device(ssg_ctx *ctx, const uint32_t *tileDev, int
     out->maxId = maxId;
     out->countNew = (uint32_t)ctx->hostCounters[C_SCRATCH1];
     out->numPairs = numPairs;
+    out->maxRankInTrim = (uint32_t)ctx->hostCounters[C_MAXRANKTRIM];
     ctx->stitchLen = len;
     ctx->stitchPairs = numPairs;
     return SSG_OK;
@@ -421,16 +431,17 @@ k_apply_lut_window4(const unsigned *__restrict__ tile, int64_t xsize, const unsi
     }
 }
 
-// lut = offset + rank where the tile numbered the segment itself (rel = rank there, 0 elsewhere;
-// rel == nullptr: every label numbers itself, the simple recode), then the ids of the crossing
-// segments over it
+// lut = offset + rank where the tile numbered the segment itself (flags == nullptr: every label
+// numbers itself, the simple recode), then the ids of the crossing segments over it
 __global__ void __launch_bounds__(256)
-k_rel_to_lut(unsigned *lut, int64_t n, unsigned offset, int identity)
+k_rel_to_lut(unsigned *lut, const unsigned char *__restrict__ flags, int64_t n, unsigned offset)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned r = identity ? (unsigned)i : lut[i];
-    lut[i] = r ? r + offset : 0u;
+    unsigned v;
+    if (flags) v = (flags[i] & SSG_SEG_NUMBERED) ? lut[i] + offset : 0u;
+    else v = i ? (unsigned)i + offset : 0u;
+    lut[i] = v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -463,7 +474,8 @@ extern "C" int ssg_apply_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64
 }
 
 extern "C" int ssg_apply_rel_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize, int64_t xsize,
-                                        const uint32_t *relHost, uint32_t maxId, uint32_t offset, int64_t nCross,
+                                        const uint32_t *rankHost, const uint8_t *flagsHost, uint32_t maxId,
+                                        uint32_t offset, int64_t nCross,
                                         const uint32_t *crossLabelsHost, const uint32_t *crossIdsHost,
                                         int64_t top, int64_t bottom, int64_t left, int64_t right,
                                         uint32_t *outDev, int64_t outStride, uint64_t *histDev, int64_t histLen)
@@ -471,24 +483,32 @@ extern "C" int ssg_apply_rel_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, i
     if (!ctx) return SSG_ERR_ARG;
     ctx->err.clear();
     SSG_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!tileDev || !outDev || nCross < 0 || (nCross && (!crossLabelsHost || !crossIdsHost)))
+    if (!tileDev || !outDev || nCross < 0 || (nCross && (!crossLabelsHost || !crossIdsHost)) || (rankHost && !flagsHost))
         SSG_FAIL(ctx, SSG_ERR_ARG, "null pointer argument");
     if (top < 0 || left < 0 || bottom > ysize || right > xsize || top > bottom || left > right) SSG_FAIL(ctx, SSG_ERR_ARG, "bad window");
     for (int64_t i = 0; i < nCross; i++)
         if (crossLabelsHost[i] > maxId) SSG_FAIL(ctx, SSG_ERR_ARG, "crossing label %u above maxId %u", crossLabelsHost[i], maxId);
     SSG_TRY(ssg_scratch_reset(ctx));
     const int64_t n = (int64_t)maxId + 1;
-    SSG_TRY(ssg_reserve(ctx, ctx->lut, (size_t)(n + 2 * nCross + 2) * sizeof(unsigned)));
-    unsigned *lut = bufp<unsigned>(ctx->lut), *crossDev = lut + n;
-    ctx->lutStage.clear();
-    if (relHost) ctx->lutStage.assign(relHost, relHost + n);
-    const size_t relLen = ctx->lutStage.size();
-    ctx->lutStage.insert(ctx->lutStage.end(), crossLabelsHost, crossLabelsHost + nCross);
-    ctx->lutStage.insert(ctx->lutStage.end(), crossIdsHost, crossIdsHost + nCross);
-    if (relLen) SSG_CUDA(ctx, cudaMemcpyAsync(lut, ctx->lutStage.data(), relLen * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-    if (nCross) SSG_CUDA(ctx, cudaMemcpyAsync(crossDev, ctx->lutStage.data() + relLen, (size_t)nCross * 2 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t flagWords = rankHost ? ((size_t)n + 3) / 4 : 0;
+    SSG_TRY(ssg_reserve(ctx, ctx->lut, ((size_t)n + 2 * (size_t)nCross + flagWords + 2) * sizeof(unsigned)));
+    unsigned *lut = bufp<unsigned>(ctx->lut), *crossDev = lut + n, *flagsDev = crossDev + 2 * nCross;
+    // one staging vector (it must outlive the asynchronous copies): rank | labels | ids | flags
+    const size_t relLen = rankHost ? (size_t)n : 0;
+    ctx->lutStage.resize(relLen + 2 * (size_t)nCross + flagWords);
+    unsigned *st = ctx->lutStage.data();
+    if (rankHost) {
+        memcpy(st, rankHost, relLen * sizeof(unsigned));
+        memcpy(st + relLen + 2 * nCross, flagsHost, (size_t)n);
+    }
+    if (nCross) {
+        memcpy(st + relLen, crossLabelsHost, (size_t)nCross * sizeof(unsigned));
+        memcpy(st + relLen + nCross, crossIdsHost, (size_t)nCross * sizeof(unsigned));
+    }
+    if (relLen) SSG_CUDA(ctx, cudaMemcpyAsync(lut, st, relLen * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    if (nCross + flagWords) SSG_CUDA(ctx, cudaMemcpyAsync(crossDev, st + relLen, (2 * (size_t)nCross + flagWords) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     SSG_PROF_BEGIN(ctx, "k_rel_to_lut");
-    k_rel_to_lut<<<gridFor(n, 256), 256, 0, ctx->stream>>>(lut, n, offset, relHost ? 0 : 1);
+    k_rel_to_lut<<<gridFor(n, 256), 256, 0, ctx->stream>>>(lut, rankHost ? reinterpret_cast<const unsigned char *>(flagsDev) : nullptr, n, offset);
     SSG_LAUNCHED(ctx);
     if (nCross) {
         SSG_PROF_BEGIN(ctx, "k_lut_overrides");

@@ -38,42 +38,100 @@ def rowMajor(tileInfo):
     return sorted(tileInfo.tiles.keys(), key=lambda cr: (cr[1], cr[0]))
 
 
-# cost of segmenting a tile, in arbitrary units: a fixed part (about a hundred dependent phases of
-# the merge kernel, whatever the tile's size) plus a part per pixel; measured on B200 as
-# 1.2 ms + 0.13 ms per megapixel
-TILE_COST_FIXED = 1.2
-TILE_COST_PER_MPIX = 0.13
+# cost of segmenting a tile, in arbitrary units: a fixed part (the dependent phases of the merge
+# kernels, whatever the tile's size) plus a part per pixel; measured on B200 (round 2 kernels) as
+# 0.5 ms + 0.095 ms per megapixel
+TILE_COST_FIXED = 0.5
+TILE_COST_PER_MPIX = 0.095
+
+
+def _tileCost(t):
+    return TILE_COST_FIXED + TILE_COST_PER_MPIX * t[2] * t[3] / 1e6
+
+
+def _splitBalanced(weights, k):
+    """Cut the list into k contiguous non-empty groups with the smallest possible largest sum;
+    returns the group index of every element."""
+    n = len(weights)
+    pre = numpy.concatenate([[0.0], numpy.cumsum(weights)])
+    INF = float('inf')
+    best = [[INF] * (n + 1) for _ in range(k + 1)]
+    cut = [[0] * (n + 1) for _ in range(k + 1)]
+    best[0][0] = 0.0
+    for g in range(1, k + 1):
+        for i in range(g, n - (k - g) + 1):
+            for j in range(g - 1, i):
+                v = max(best[g - 1][j], pre[i] - pre[j])
+                if v < best[g][i]:
+                    (best[g][i], cut[g][i]) = (v, j)
+    groups = [0] * n
+    i = n
+    for g in range(k, 0, -1):
+        j = cut[g][i]
+        for e in range(j, i):
+            groups[e] = g - 1
+        i = j
+    return groups
+
+
+def partitionChunks(tileInfo, world):
+    """owner rank of every tile: contiguous chunks of the row-major tile list (tiling.py:892-893)
+    with as equal a share of the segmentation cost as the tile boundaries allow."""
+    order = rowMajor(tileInfo)
+    groups = _splitBalanced([_tileCost(tileInfo.tiles[cr]) for cr in order], min(world, len(order)))
+    return dict((cr, g) for (cr, g) in zip(order, groups))
 
 
 def partitionTiles(tileInfo, world):
     """
-    owner rank of every tile: contiguous chunks of the row-major tile list (tiling.py:892-893)
-    with as equal a share of the segmentation cost as the tile boundaries allow.  Contiguous
-    chunks keep most neighbours on the same GPU.
+    owner rank of every tile.  The ranks form a grid of pr x pc rectangular blocks of tiles
+    (pr * pc = world, ranks numbered row-major over the blocks): a rank then has remote upper or
+    left neighbours only along the top row and left column of its block, and only those tiles
+    have to wait for the other ranks before their stitch tables can be made.  Among the grids
+    that fit, the one with the smallest largest block cost wins, fewer boundary tiles on ties.
+    Without a fitting grid (or with one block per rank row anyway) the row-major list is cut
+    into contiguous chunks.  The reference deals tiles round-robin over its workers
+    (tiling.py:892-893); which worker segments a tile does not change the result.
     """
-    order = rowMajor(tileInfo)
-    cost = numpy.array([TILE_COST_FIXED + TILE_COST_PER_MPIX * tileInfo.tiles[cr][2] * tileInfo.tiles[cr][3] / 1e6
-        for cr in order], dtype=numpy.float64)
-    cum = numpy.cumsum(cost)
-    total = cum[-1]
-    owner = {}
-    for (i, cr) in enumerate(order):
-        mid = cum[i] - cost[i] / 2.0          # the rank whose share holds the tile's midpoint
-        owner[cr] = min(world - 1, int(mid * world / total))
-    # a rank must not be skipped: make the assignment monotone and gap-free
-    last = 0
-    for cr in order:
-        r = owner[cr]
-        if r > last + 1:
-            r = last + 1
-        owner[cr] = r
-        last = r
-    return owner
+    (nrows, ncols) = (tileInfo.nrows, tileInfo.ncols)
+    if world <= 1:
+        return dict((cr, 0) for cr in tileInfo.tiles)
+    heights = [tileInfo.tiles[(0, r)][3] for r in range(nrows)]
+    widths = [tileInfo.tiles[(c, 0)][2] for c in range(ncols)]
+    best = None
+    for pr in range(1, world + 1):
+        if world % pr:
+            continue
+        pc = world // pr
+        if pr > nrows or pc > ncols:
+            continue
+        rg = _splitBalanced([h + 1e-9 for h in heights], pr)
+        cg = _splitBalanced([w + 1e-9 for w in widths], pc)
+        cost = numpy.zeros(world)
+        boundary = 0
+        for ((c, r), t) in tileInfo.tiles.items():
+            cost[rg[r] * pc + cg[c]] += _tileCost(t)
+            if (r > 0 and rg[r - 1] != rg[r]) or (c > 0 and cg[c - 1] != cg[c]):
+                boundary += 1
+        key = (round(float(cost.max()), 6), boundary)
+        if best is None or key < best[0]:
+            best = (key, rg, cg, pc)
+    chunks = partitionChunks(tileInfo, world)
+    if best is None:
+        return chunks
+    (key, rg, cg, pc) = best
+    chunkCost = numpy.zeros(world)
+    for (cr, g) in chunks.items():
+        chunkCost[g] += _tileCost(tileInfo.tiles[cr])
+    if chunkCost.max() < 0.8 * key[0]:
+        return chunks           # the blocks are much less even than the chunks would be
+    return dict(((c, r), rg[r] * pc + cg[c]) for (c, r) in tileInfo.tiles)
 
 
 class TileTable(object):
     """The host copy of what ssg_tile_tables_device computed for one tile."""
-    def __init__(self, maxId, countNew, rank, flags, pairKeys, pairCounts):
+    def __init__(self, maxId, countNew, rank, flags, pairKeys, pairCounts, maxRankInTrim=None):
+        self.givenMaxRankInTrim = maxRankInTrim      # (computed with the tables on the device)
         self.maxId = int(maxId)
         self.countNew = int(countNew)
         self.rank = numpy.ascontiguousarray(rank, dtype=numpy.uint32)
@@ -84,8 +142,10 @@ class TileTable(object):
 
     @property
     def maxRankInTrim(self):
-        sel = (self.flags & (_lib.SEG_NUMBERED | _lib.SEG_INTRIM)) == (_lib.SEG_NUMBERED | _lib.SEG_INTRIM)
-        return int(self.rank[sel].max()) if sel.any() else 0
+        if self.givenMaxRankInTrim is not None:
+            return int(self.givenMaxRankInTrim)
+        both = numpy.uint8(_lib.SEG_NUMBERED | _lib.SEG_INTRIM)
+        return int(numpy.max(self.rank, where=(self.flags & both) == both, initial=0))
 
     @property
     def maxLabelInTrim(self):
@@ -93,19 +153,23 @@ class TileTable(object):
         return int(sel[-1]) if len(sel) else 0
 
     def prepare(self):
-        """Everything of the tile's lut that does not depend on the id offset, so that it can be
-        worked out as soon as the tables exist (while other tiles are still being segmented):
-        (rank where numbered else 0, 1 where numbered else 0, positions of the crossing segments)"""
+        """What the resolve needs of the tile besides look-ups of single labels, worked out once
+        (as soon as the tables exist, while other tiles are still being segmented): the labels of
+        the crossing segments, which of them lie in the trimmed window, the highest rank in the
+        window, the decoded votes.  Nothing here is longer than a pass over the flag bytes."""
         if getattr(self, '_prepared', None) is None:
-            numbered = ((self.flags & _lib.SEG_NUMBERED) != 0)
-            rel = numpy.where(numbered, self.rank, numpy.uint32(0)).astype(numpy.uint32)
-            crossing = numpy.flatnonzero((self.flags & KEY_FLAGS) != 0)
-            self._prepared = (rel, numbered.astype(numpy.uint32), crossing)
+            crossing = numpy.flatnonzero((self.flags & numpy.uint8(KEY_FLAGS)) != 0)
+            self._prepared = crossing
             self.crossInTrimMask = (self.flags[crossing] & _lib.SEG_INTRIM) != 0
             self.crossingInTrim = crossing[self.crossInTrimMask]
             self.cachedMaxRankInTrim = self.maxRankInTrim
             self.pairs()
         return self._prepared
+
+    def rel(self):
+        """rank where the tile numbered the segment itself, 0 elsewhere (a full-length array:
+        only for building a whole lut on the host)"""
+        return numpy.where((self.flags & _lib.SEG_NUMBERED) != 0, self.rank, numpy.uint32(0)).astype(numpy.uint32)
 
     def pairs(self):
         """(isLeft, segment, neighbour label, count) of the votes, decoded once."""
@@ -202,7 +266,7 @@ class LazyResolver(object):
             if self.simple:
                 crossing = numpy.zeros(0, dtype=numpy.int64)
             else:
-                crossing = tb.prepare()[2]
+                crossing = tb.prepare()
             self.cross[cr] = (crossing, numpy.full(len(crossing), self.UNKNOWN, dtype=self.dtype))
         return self.cross[cr]
 
@@ -223,8 +287,8 @@ class LazyResolver(object):
             out[labels == 0] = 0
             return out
         (crossing, vals) = self._crossOf(cr)
-        rel = tb.prepare()[0][labels].astype(self.dtype)
-        out = numpy.where(rel > 0, rel + off, self.dtype.type(0))
+        numbered = (tb.flags[labels] & _lib.SEG_NUMBERED) != 0
+        out = numpy.where(numbered, tb.rank[labels].astype(self.dtype) + off, self.dtype.type(0))
         (pos, isCross) = self._pos(crossing, labels)
         out[isCross] = vals[pos[isCross]]
         return out
@@ -346,8 +410,8 @@ class LazyResolver(object):
             lut = numpy.arange(tb.maxId + 1, dtype=self.dtype) + off
             lut[0] = 0
             return lut
-        (rel, isNumbered, crossing) = tb.prepare()
-        lut = rel.astype(self.dtype) + isNumbered.astype(self.dtype) * off
+        rel = tb.rel().astype(self.dtype)
+        lut = numpy.where(rel > 0, rel + off, self.dtype.type(0))
         (cl, cv) = self.crossingIds(cr)
         lut[cl] = cv
         return lut
@@ -651,8 +715,8 @@ class ShardedStitch(object):
             lut = numpy.arange(tb.maxId + 1, dtype=numpy.uint32) + numpy.uint32(offset)
             lut[0] = 0
             return lut
-        (rel, isNumbered, crossing) = tb.prepare()
-        lut = rel + isNumbered * numpy.uint32(offset)
+        rel = tb.rel()
+        lut = numpy.where(rel > 0, rel + numpy.uint32(offset), numpy.uint32(0)).astype(numpy.uint32)
         lut[crossFinal[0]] = crossFinal[1]
         return lut
 
@@ -733,8 +797,9 @@ class ShardedStitch(object):
         first = True
         for _round in range(len(self.order) + 4):
             resolver.requests = {}
-            for cr in self.mine:          # (entries settled earlier are kept)
-                resolver.settle(cr)
+            with self._timed('resolve_settle'):
+                for cr in self.mine:          # (entries settled earlier are kept)
+                    resolver.settle(cr)
             msg = []
             if first:
                 head = [len(self.mine)]
@@ -762,7 +827,8 @@ class ShardedStitch(object):
             for (cr, parts) in sorted(resolver.requests.items()):
                 labels = numpy.unique(numpy.concatenate(parts))
                 msg += [numpy.array([cr[0], cr[1], len(labels)], dtype=numpy.int64), labels]
-            allReq = comm.allgatherArray(numpy.concatenate(msg))
+            with self._timed('resolve_gather%d' % min(_round, 2)):
+                allReq = comm.allgatherArray(numpy.concatenate(msg))
             asked = []
             states = []
             for a in allReq:
@@ -798,7 +864,9 @@ class ShardedStitch(object):
                 if self.owner[cr] == comm.rank:
                     (lab, vals) = resolver.answer(cr, labels)
                     ans += [numpy.array([cr[0], cr[1], len(lab)], dtype=numpy.int64), lab, vals.astype(numpy.int64)]
-            for a in comm.allgatherArray(numpy.concatenate(ans) if ans else numpy.zeros(0, numpy.int64)):
+            with self._timed('resolve_answers'):
+                allAns = comm.allgatherArray(numpy.concatenate(ans) if ans else numpy.zeros(0, numpy.int64))
+            for a in allAns:
                 o = 0
                 while o < len(a):
                     (c, r, n) = (int(v) for v in a[o:o + 3])

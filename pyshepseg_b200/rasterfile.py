@@ -51,10 +51,11 @@ class RasterSource(object):
 
 
 class MemoryRaster(RasterSource):
-    """A (count, ysize, xsize) array as a raster.  With `yoff` / `fullYsize` the array is the row
-    band [yoff, yoff + ysize) of a taller raster of fullYsize rows: what one rank of a sharded
-    run holds of the mosaic (window reads are then relative to the band)."""
-    def __init__(self, img, nodata=None, yoff=0, fullYsize=None):
+    """A (count, ysize, xsize) array as a raster.  With `yoff` / `fullYsize` (and `xoff` /
+    `fullXsize`) the array is the window [yoff, yoff + ysize) x [xoff, xoff + xsize) of a larger
+    raster of fullYsize x fullXsize: what one rank of a sharded run holds of the mosaic (window
+    reads are then relative to it)."""
+    def __init__(self, img, nodata=None, yoff=0, fullYsize=None, xoff=0, fullXsize=None):
         img = numpy.asarray(img)
         if img.ndim == 2:
             img = img[None]
@@ -64,6 +65,8 @@ class MemoryRaster(RasterSource):
         self.nodata = [nodata] * self.count
         self.yoff = int(yoff)
         self.fullYsize = self.ysize if fullYsize is None else int(fullYsize)
+        self.xoff = int(xoff)
+        self.fullXsize = self.xsize if fullXsize is None else int(fullXsize)
 
     def readWindow(self, bandNumbers, xoff, yoff, xsize, ysize, out=None):
         if out is None:
@@ -279,20 +282,22 @@ class RasterSink(object):
 
 class MemorySink(RasterSink):
     """The output raster as a numpy array.  `array` (optional) is caller-owned memory to write
-    into, e.g. pinned host memory; with `yoff` it is the row band of a taller mosaic that starts
-    at mosaic row yoff (one rank of a sharded run).  Overviews are kept per level in
+    into, e.g. pinned host memory; with `yoff` / `xoff` it is the window of a larger mosaic that
+    starts at mosaic row yoff and column xoff (one rank of a sharded run).  Overviews are kept per level in
     `overviews` when `levels` is given (tiling.py:1360-1383)."""
     levels = ()
     overviews = {}
     yoff = 0
+    xoff = 0
 
-    def __init__(self, xsize, ysize, dtype=numpy.uint32, array=None, yoff=0, levels=None):
+    def __init__(self, xsize, ysize, dtype=numpy.uint32, array=None, yoff=0, levels=None, xoff=0):
         if array is None:
             array = numpy.zeros((ysize, xsize), dtype=dtype)
         elif array.shape != (ysize, xsize):
             raise RasterError('array of shape %s given for a %d x %d raster' % (array.shape, ysize, xsize))
         self.array = array
         self.yoff = int(yoff)
+        self.xoff = int(xoff)
         self.metadata = {}
         self.nodata = None
         self.hist = None

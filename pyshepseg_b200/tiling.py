@@ -400,14 +400,14 @@ class _RasterUploader(object):
     order in which the tiles need them (a stream of its own), and a tile is gathered out of the
     device copy (device-to-device) as soon as its cells have landed.
     """
-    def __init__(self, slot, hostBase, bandNumbers, ysize, xsize, item, devPtr, tiles, yoff):
+    def __init__(self, slot, hostBase, bandNumbers, ysize, xsize, item, devPtr, tiles, yoff, xoff=0):
         self.slot = slot
         self.hostBase = hostBase
         self.planes = [b - 1 for b in bandNumbers]      # planes of the host raster, in order
         (self.ysize, self.xsize, self.item) = (ysize, xsize, item)
         self.devPtr = devPtr                             # (len(bandNumbers), ysize, xsize)
-        # tiles: [(key, xpos, ypos - yoff, xsize, ysize)] in the order they will be segmented
-        self.tiles = [(k, x, y - yoff, xs, ys) for (k, x, y, xs, ys) in tiles]
+        # tiles: [(key, xpos - xoff, ypos - yoff, xsize, ysize)] in the order they will be segmented
+        self.tiles = [(k, x - xoff, y - yoff, xs, ys) for (k, x, y, xs, ys) in tiles]
         xs = sorted(set([0, xsize] + [t[1] for t in self.tiles] + [t[1] + t[3] for t in self.tiles]))
         ys = sorted(set([0, ysize] + [t[2] for t in self.tiles] + [t[2] + t[4] for t in self.tiles]))
         (self.xEdges, self.yEdges) = (xs, ys)
@@ -549,7 +549,8 @@ class TiledSegmenter(object):
         nB = len(self.bandNumbers)
         nPix = tile.ysize * tile.xsize
         direct = self._directSource()
-        ypos = tile.ypos - getattr(self.src, 'yoff', 0)   # a rank of a sharded run holds a row band
+        ypos = tile.ypos - getattr(self.src, 'yoff', 0)   # a rank of a sharded run holds a window
+        xpos = tile.xpos - getattr(self.src, 'xoff', 0)
         with self.timings.interval('reading'):
             if direct is not None:
                 # the raster is addressable memory (HBM, or host memory that cudaMemcpy2D can
@@ -564,13 +565,13 @@ class TiledSegmenter(object):
                 for (i, b) in enumerate(self.bandNumbers):
                     plane = i if up is not None else b - 1
                     srcPtr = base + (plane * self.src.ysize * self.src.xsize +
-                        ypos * self.src.xsize + tile.xpos) * item
+                        ypos * self.src.xsize + xpos) * item
                     ctx.call(copy, imgDev + i * nPix * item, tile.xsize * item, srcPtr,
                         self.src.xsize * item, tile.xsize * item, tile.ysize)
             else:
                 with self.readSemaphore:
                     img = slot.pinnedFor(nB * nPix, dtype).reshape(nB, tile.ysize, tile.xsize)
-                    self.src.readWindow(self.bandNumbers, tile.xpos, ypos, tile.xsize, tile.ysize,
+                    self.src.readWindow(self.bandNumbers, xpos, ypos, tile.xsize, tile.ysize,
                         out=img)
         self.mark('tile %d,%d read issued' % (tile.col, tile.row))
         with self.timings.interval('segmentation'):
@@ -625,7 +626,7 @@ class TiledSegmenter(object):
         tiles = [(cr, self.tiles[cr].xpos, self.tiles[cr].ypos, self.tiles[cr].xsize, self.tiles[cr].ysize)
             for cr in order]
         self.uploader = _RasterUploader(slot, direct[0], self.bandNumbers, self.src.ysize, self.src.xsize,
-            dtype.itemsize, state.rasterBuf[1], tiles, getattr(self.src, 'yoff', 0))
+            dtype.itemsize, state.rasterBuf[1], tiles, getattr(self.src, 'yoff', 0), getattr(self.src, 'xoff', 0))
         self.uploader.start()
 
     def _finishUpload(self):
@@ -737,14 +738,15 @@ class TiledSegmenter(object):
                 _lib.ptr(pairCounts))
         self.d2hBytes += rank.nbytes + flags.nbytes + pairKeys.nbytes + pairCounts.nbytes
         from . import distributed
-        return distributed.TileTable(tables.maxId, tables.countNew, rank, flags, pairKeys, pairCounts)
+        return distributed.TileTable(tables.maxId, tables.countNew, rank, flags, pairKeys, pairCounts,
+            maxRankInTrim=int(tables.maxRankInTrim))
 
     def applyLut(self, slot, tile, lut, maxId, sink, hist, histLen, deferred=None, fetchLen=0, rel=None):
         """Device phase 2: final ids over the trimmed window, on the device, then to the sink.
         deferred (a list, for the last tile of a run): if the window can travel on its own, the
         histogram copy is queued BEFORE it (mark 0), the window copy is left in flight (mark 1)
         and 'window' is appended to the list: the caller works on the histogram meanwhile.
-        rel = (rel, offset, crossLabels, crossIds) instead of lut: the lut is put together on
+        rel = (rank, flags, offset, crossLabels, crossIds) instead of lut: the lut is put together on
         the device (ssg_apply_rel_lut_device)."""
         ctx = slot.ctx
 
@@ -754,18 +756,19 @@ class TiledSegmenter(object):
                     int(maxId), top, bottom, left, right, out, outStride, hist.dev, hist.cap)
                 self.h2dBytes += lut.nbytes
             else:
-                (relArr, offset, crossLabels, crossIds) = rel
+                (rankArr, flagsArr, offset, crossLabels, crossIds) = rel
                 ctx.call('ssg_apply_rel_lut_device', tile.buf[1], tile.ysize, tile.xsize,
-                    None if relArr is None else _lib.ptr(relArr), int(maxId), int(offset), len(crossLabels),
+                    None if rankArr is None else _lib.ptr(rankArr),
+                    None if rankArr is None else _lib.ptr(flagsArr), int(maxId), int(offset), len(crossLabels),
                     _lib.ptr(crossLabels) if len(crossLabels) else None,
                     _lib.ptr(crossIds) if len(crossLabels) else None,
                     top, bottom, left, right, out, outStride, hist.dev, hist.cap)
-                self.h2dBytes += (0 if relArr is None else relArr.nbytes) + 8 * len(crossLabels)
+                self.h2dBytes += (0 if rankArr is None else rankArr.nbytes + flagsArr.nbytes) + 8 * len(crossLabels)
         (top, bottom, left, right) = tileMargins(self.tileInfo, tile.col, tile.row, tile.xsize,
             tile.ysize, self.overlapSize)
         (wr, wc) = (bottom - top, right - left)
         hist.ensure(ctx, histLen)
-        xout = tile.xpos + left
+        xout = tile.xpos + left - getattr(sink, 'xoff', 0)
         yout = tile.ypos + top - getattr(sink, 'yoff', 0)
         if isinstance(sink, DeviceMosaicSink):
             # the mosaic lives in HBM: write the window in place
@@ -1010,7 +1013,7 @@ class TiledSegmenter(object):
                 if len(crossIds):
                     top = max(top, int(crossIds.max()))
                 seg.applyLut(main, t, None, tb.maxId, sink, hist, top + 1, rel=(
-                    None if seg.simple else tb.prepare()[0], offset,
+                    None if seg.simple else tb.rank, tb.flags, offset,
                     numpy.ascontiguousarray(crossLabels, dtype=numpy.uint32),
                     numpy.ascontiguousarray(crossIds, dtype=numpy.uint32)))
 
@@ -1106,9 +1109,10 @@ class DeviceRaster(rasterfile.RasterSource):
     """A band-sequential (count, ysize, xsize) raster that already lives in GPU memory
     (devPtr is a device pointer on the segmenting GPU).  Used to measure the path with its
     input resident in HBM; tiles are gathered with device-to-device copies."""
-    def __init__(self, devPtr, count, ysize, xsize, dtype, nodata=None, yoff=0):
+    def __init__(self, devPtr, count, ysize, xsize, dtype, nodata=None, yoff=0, xoff=0):
         self.devPtr = int(devPtr)
-        self.yoff = int(yoff)        # mosaic row of the buffer's first row (a rank's row band)
+        self.yoff = int(yoff)        # mosaic row / column of the buffer's first pixel (a rank's window)
+        self.xoff = int(xoff)
         (self.count, self.ysize, self.xsize) = (int(count), int(ysize), int(xsize))
         self.dtype = numpy.dtype(dtype)
         self.nodata = [nodata] * self.count
@@ -1117,10 +1121,11 @@ class DeviceRaster(rasterfile.RasterSource):
 class DeviceMosaicSink(rasterfile.RasterSink):
     """A uint32 (ysize, xsize) output mosaic in GPU memory: the stitch writes the trimmed
     windows in place and nothing but the small per-tile tables crosses PCIe."""
-    def __init__(self, devPtr, xsize, ysize, yoff=0):
+    def __init__(self, devPtr, xsize, ysize, yoff=0, xoff=0):
         self.devPtr = int(devPtr)
         (self.xsize, self.ysize) = (int(xsize), int(ysize))
-        self.yoff = int(yoff)        # mosaic row of the buffer's first row (a rank's row band)
+        self.yoff = int(yoff)        # mosaic row / column of the buffer's first pixel (a rank's window)
+        self.xoff = int(xoff)
         self.metadata = {}
         self.hist = None
 
@@ -1283,6 +1288,7 @@ def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
         comm = getattr(concurrencyCfg, 'comm', None)
         sharded = comm is not None and comm.world > 1
         fullYsize = getattr(src, 'fullYsize', src.ysize)
+        fullXsize = getattr(src, 'fullXsize', src.xsize)
         if kmeansObj is None:
             if sharded:
                 raise PyShepSegTilingError("a sharded run needs kmeansObj (fit on one rank, "
@@ -1292,13 +1298,13 @@ def doTiledShepherdSegmentation(infile, outfile, tileSize=DFLT_TILESIZE,
                     bandNumbers, numClusters, subsamplePcnt, imgNullVal, fixedKMeansInit)
         elif imgNullVal is None:
             imgNullVal = getImgNullValue(src, bandNumbers)
-        tileInfo = getTilesForFile((src.xsize, fullYsize), tileSize, overlapSize)
+        tileInfo = getTilesForFile((fullXsize, fullYsize), tileSize, overlapSize)
         if verbose:
             print("Found {} tiles, with {} rows and {} cols".format(tileInfo.getNumTiles(),
                 tileInfo.nrows, tileInfo.ncols))
         msd = shepseg.autoMaxSpectralDiff(kmeansObj, maxSpectralDiff, spectDistPcntile)
         try:
-            sink = rasterfile.createRaster(outfile, src.xsize, fullYsize, outputDriver,
+            sink = rasterfile.createRaster(outfile, fullXsize, fullYsize, outputDriver,
                 creationOptions, source=src)
         except rasterfile.RasterError as e:
             raise PyShepSegTilingError(str(e))

@@ -86,6 +86,19 @@ class NumpyOps(object):
         self.out[y + top:y + bottom, x + left:x + right] = lut[self.segs[cr][top:bottom, left:right]]
 
 
+class NumpyRelOps(NumpyOps):
+    """the same with the lut put together from rank + offset and the crossing segments' ids, as
+    ssg_apply_rel_lut_device does"""
+    def applyRel(self, cr, offset, crossLabels, crossIds, tb):
+        numbered = (tb.flags & 2) != 0
+        lut = numpy.where(numbered, tb.rank + numpy.uint32(offset), 0).astype(numpy.uint32)
+        if self.simple:
+            lut = numpy.arange(tb.maxId + 1, dtype=numpy.uint32) + numpy.uint32(offset)
+            lut[0] = 0
+        lut[crossLabels] = crossIds
+        self.apply(cr, lut, tb)
+
+
 def _rank_main(rank, world, port, case, forceSequential, resq):
     import torch.distributed as dist
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
@@ -102,7 +115,8 @@ def _rank_main(rank, world, port, case, forceSequential, resq):
         # a rank only ever touches the labels of its own tiles (remote strips arrive by message)
         segs = dict((cr, allSegs[cr]) for cr in st.mine)
         out = numpy.zeros((nR, nC), dtype=numpy.uint32)
-        ops = NumpyOps(ti, segs, overlap, out)
+        ops = NumpyOps(ti, segs, overlap, out) if seed % 2 else NumpyRelOps(ti, segs, overlap, out)
+        ops.simple = simple
         (maxSegId, offsets, luts) = st.run(ops)
         total = comm.allreduceSum(out.astype(numpy.int64))    # windows are disjoint
         if rank == 0:
@@ -162,17 +176,42 @@ def test_sharded_stitch_gloo(case):
     assert usedFallback == fallbackExpected
 
 
-def test_partition_is_contiguous_and_balanced():
+def _costs(ti, owner, world):
+    cost = numpy.zeros(world)      # the partition balances the modelled segmentation cost
+    for (cr, t) in ti.tiles.items():
+        cost[owner[cr]] += distributed.TILE_COST_FIXED + distributed.TILE_COST_PER_MPIX * t[2] * t[3] / 1e6
+    return cost
+
+
+def test_partition_is_blocks_and_balanced():
+    ti = tiling.getTilesForFile((40000, 40000), 4096, 1024)
+    for world in (1, 2, 4, 8):
+        owner = distributed.partitionTiles(ti, world)
+        assert set(owner.values()) == set(range(world))
+        for rank in range(world):      # every rank owns a full rectangle of tiles
+            mine = [cr for cr in ti.tiles if owner[cr] == rank]
+            cols = sorted(set(c for (c, r) in mine))
+            rows = sorted(set(r for (c, r) in mine))
+            assert len(mine) == len(cols) * len(rows)
+            assert cols == list(range(cols[0], cols[-1] + 1)) and rows == list(range(rows[0], rows[-1] + 1))
+        cost = _costs(ti, owner, world)
+        assert cost.max() / cost.mean() < 1.15
+    # no grid of 7 blocks fits 3 x 3 tiles: contiguous chunks of the row-major list
+    ti = tiling.getTilesForFile((12000, 12000), 4096, 512)
+    assert (ti.nrows, ti.ncols) == (3, 3)
+    owner = distributed.partitionTiles(ti, 7)
+    ranks = [owner[cr] for cr in distributed.rowMajor(ti)]
+    assert ranks == sorted(ranks) and set(ranks) == set(range(7))
+
+
+def test_chunk_partition_is_contiguous_and_balanced():
     ti = tiling.getTilesForFile((40000, 40000), 4096, 1024)
     order = distributed.rowMajor(ti)
     for world in (1, 2, 4, 8):
-        owner = distributed.partitionTiles(ti, world)
+        owner = distributed.partitionChunks(ti, world)
         ranks = [owner[cr] for cr in order]
         assert ranks == sorted(ranks) and set(ranks) == set(range(world))
-        cost = numpy.zeros(world)      # the partition balances the modelled segmentation cost
-        for cr in order:
-            cost[owner[cr]] += distributed.TILE_COST_FIXED + \
-                distributed.TILE_COST_PER_MPIX * ti.tiles[cr][2] * ti.tiles[cr][3] / 1e6
+        cost = _costs(ti, owner, world)
         assert cost.max() / cost.mean() < 1.05
 
 
