@@ -465,7 +465,27 @@ def run_ours(args, wl):
         (x0, x1) = (min(t[0] for t in mineT), max(t[0] + t[2] for t in mineT))
     (bandRows, bandCols) = (y1 - y0, x1 - x0)      # the window of the raster this rank's tiles cover
     pinnedImg = _lib.PinnedArray((nB, bandRows, bandCols), numpy.uint16)
-    if world == 1:
+    if wl.get('strong'):
+        # the 40000 x 40000 mosaic: one synthetic 10000 x 10000 patch (rank 0 makes it, NCCL hands
+        # it round) laid out 4 x 4 with every other copy mirrored, so that the raster is continuous
+        # across the seams; a rank cuts its own window out of the patch on its GPU
+        P = min(10000, nR)
+        patch = torch.empty((nB, P, P), dtype=torch.int16, device='cuda')
+        if rank == 0:
+            patch.copy_(torch.from_numpy(synth.synth_tiled(P, P, nB, seed=1).view(numpy.int16)))
+        if dist is not None:
+            dist.broadcast(patch.view(torch.uint8), 0)
+
+        def mirrored(lo, hi):
+            i = torch.arange(lo, hi, device='cuda') % (2 * P)
+            return torch.where(i < P, i, 2 * P - 1 - i)
+        (ri, ci) = (mirrored(y0, y1), mirrored(x0, x1))
+        img = pinnedImg.array
+        for b in range(nB):
+            img[b] = patch[b].index_select(0, ri).index_select(1, ci).cpu().numpy().view(numpy.uint16)
+        del patch
+        torch.cuda.empty_cache()
+    elif world == 1:
         img = make_scene(wl, seed=1, out=pinnedImg.array)
     else:
         img = synth.synth_window(nR, nC, nB, 1, y0, x0, bandRows, bandCols, out=pinnedImg.array)

@@ -641,6 +641,7 @@ class ShardedStitch(object):
         self.usedFallback = False
         self.forceSequential = False    # (tests) take the fall-back even if the check passes
         self.earlyTables = {}
+        self.received = None
         symbolic = dict((cr, i << self.SHIFT) for (i, cr) in enumerate(self.order))
         self.resolver = LazyResolver({}, symbolic, simple, dtype=numpy.uint64)
 
@@ -672,6 +673,28 @@ class ShardedStitch(object):
                     recvs.append((self.owner[nb], nb, which, shape))
         return (sends, recvs)
 
+    def feedPlan(self):
+        """(own tiles whose bottom or right strip a tile of another rank needs, in row-major
+        order; after how many finished tiles every rank enters the strip exchange).  A rank that
+        segments its feeding tiles FIRST can hand the strips over while it is still busy with
+        the rest; the count is the largest number of feeding tiles any rank has, so that no rank
+        sits in the exchange long before the strips it is waiting for exist."""
+        feeds = dict((r, []) for r in range(self.comm.world))
+        if not self.simple:
+            for cr in self.order:
+                for nb in self.neighbours(cr):
+                    if nb is not None and self.owner[nb] != self.owner[cr] and nb not in feeds[self.owner[nb]]:
+                        feeds[self.owner[nb]].append(nb)
+        mine = sorted(feeds[self.comm.rank], key=lambda cr: (cr[1], cr[0]))
+        return (mine, max(len(v) for v in feeds.values()))
+
+    def exchangeStrips(self, ops):
+        """The strip exchange, callable before run() (as soon as the feeding tiles are done)."""
+        if self.received is None:
+            with self._timed('stitch_strips'):
+                self.received = self._exchangeStrips(ops)
+        return self.received
+
     def _timed(self, name):
         import contextlib
         return self.timings.interval(name) if self.timings is not None else contextlib.nullcontext()
@@ -691,8 +714,7 @@ class ShardedStitch(object):
 
     def run(self, ops):
         """returns (maxSegId, offsets of all tiles, luts of own tiles)"""
-        with self._timed('stitch_strips'):
-            received = self._exchangeStrips(ops)
+        received = self.exchangeStrips(ops)
         with self._timed('stitch_owntables'):
             tables = self._ownTables(ops, received)
         with self._timed('stitch_resolve'):

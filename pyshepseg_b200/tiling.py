@@ -1024,18 +1024,49 @@ class TiledSegmenter(object):
             hist.reset(main.ctx)
             self._profileStart(main)
             ops = Ops()
+            # Tiles that feed another rank (their bottom / right strip lies under a remote tile's
+            # overlap) are segmented first and their strips handed over while the rest is still
+            # in work; a tile gets its stitch tables as soon as it and what lies under its
+            # overlaps (own neighbours, received strips) exist.
+            (feed, exchangeAfter) = stitch.feedPlan()
+            order = feed + [cr for cr in mine if cr not in feed]
+            exchangeAfter = min(exchangeAfter, len(order))
+            tabled = set()
+
+            def tryTables():
+                for cr in mine:
+                    if cr in tabled or not self.tiles[cr].done.is_set() or self.tiles[cr].error is not None:
+                        continue
+                    args = []
+                    for (nb, which) in zip(stitch.neighbours(cr), ('bottom', 'right')):
+                        if nb is None or self.simple:
+                            args.append(None)
+                        elif stitch.owner[nb] == comm.rank:
+                            if not self.tiles[nb].done.is_set():
+                                break
+                            args.append('local')
+                        else:
+                            if stitch.received is None:
+                                break
+                            args.append(stitch.received[(nb, which)])
+                    else:
+                        tabled.add(cr)
+                        stitch.early(cr, ops.tables(cr, args[0], args[1]))
+
             with self.timings.interval('segmentation_all'):
                 if numWorkers > 0:
                     inQue = queue.Queue()
-                    for cr in mine:
+                    for cr in order:
                         inQue.put(cr)
-                    self._startUpload(state, numWorkers + 1, mine)
+                    self._startUpload(state, numWorkers + 1, order)
                     for w in range(numWorkers):
                         th = threading.Thread(target=self._worker, args=(state.slot(1 + w), pool, inQue),
                             daemon=True)
                         th.start()
                         workers.append(th)
-                for cr in mine:
+                if exchangeAfter == 0:
+                    stitch.exchangeStrips(ops)
+                for (i, cr) in enumerate(order):
                     tile = self.tiles[cr]
                     if numWorkers > 0:
                         if not tile.done.wait(cfg.tileCompletionTimeout):
@@ -1047,13 +1078,10 @@ class TiledSegmenter(object):
                                 cr[0], cr[1], tile.error))
                     else:
                         self.segmentOne(main, pool, tile)
-                    # a tile whose upper and left neighbours are this rank's own (and therefore
-                    # done: they come earlier in the order) gets its tables while the workers go on
-                    (up, left) = stitch.neighbours(cr)
-                    if all(nb is None or stitch.owner[nb] == comm.rank for nb in (up, left)):
-                        # (and its lut, as far as it hangs on own tiles only)
-                        stitch.early(cr, ops.tables(cr, None if (up is None or self.simple) else 'local',
-                            None if (left is None or self.simple) else 'local'))
+                        tile.done.set()
+                    if i + 1 == exchangeAfter:
+                        stitch.exchangeStrips(ops)
+                    tryTables()
                 for th in workers:
                     th.join()
             with self.timings.interval('stitchtiles'):
