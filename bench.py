@@ -541,6 +541,8 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    stepWalls = {}      # host wall time of every timed step of this rank
+
     def timed(stepFn, steps):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
@@ -558,6 +560,7 @@ def run_ours(args, wl):
                 sys.stderr.flush()
                 os._exit(1)
             exchange_ids(last[1])
+            stepWalls.setdefault(getattr(stepFn, '__name__', '?'), []).append(round((time.time() - t0) * 1e3, 1))
             if args.verbose_steps and rank == 0:
                 print('  step %s: %.1f ms' % (getattr(stepFn, '__name__', '?'), (time.time() - t0) * 1e3),
                     file=sys.stderr, flush=True)
@@ -678,6 +681,7 @@ def run_ours(args, wl):
                     lastRes[0].timings.makeSummaryDict().items()),
                  'e2e': dict((k, round(v['total'] * 1e3, 1)) for (k, v) in
                     lastE2E[0].timings.makeSummaryDict().items()),
+                 'step_wall_ms': stepWalls,
                  'tiles': len([cr for cr in tileInfo.tiles if owner[cr] == rank]),
                  'tile_mpix': round(sum(t[2] * t[3] for (cr, t) in tileInfo.tiles.items() if owner[cr] == rank) / 1e6, 1)}
         perRank = [None] * world

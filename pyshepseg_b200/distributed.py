@@ -54,20 +54,18 @@ def _splitBalanced(weights, k):
     returns the group index of every element."""
     n = len(weights)
     pre = numpy.concatenate([[0.0], numpy.cumsum(weights)])
-    INF = float('inf')
-    best = [[INF] * (n + 1) for _ in range(k + 1)]
-    cut = [[0] * (n + 1) for _ in range(k + 1)]
-    best[0][0] = 0.0
+    best = numpy.full((k + 1, n + 1), numpy.inf)
+    cut = numpy.zeros((k + 1, n + 1), dtype=numpy.int64)
+    best[0, 0] = 0.0
     for g in range(1, k + 1):
         for i in range(g, n - (k - g) + 1):
-            for j in range(g - 1, i):
-                v = max(best[g - 1][j], pre[i] - pre[j])
-                if v < best[g][i]:
-                    (best[g][i], cut[g][i]) = (v, j)
+            v = numpy.maximum(best[g - 1, g - 1:i], pre[i] - pre[g - 1:i])     # last group = [j, i)
+            j = int(numpy.argmin(v))
+            (best[g, i], cut[g, i]) = (v[j], j + g - 1)
     groups = [0] * n
     i = n
     for g in range(k, 0, -1):
-        j = cut[g][i]
+        j = int(cut[g, i])
         for e in range(j, i):
             groups[e] = g - 1
         i = j
@@ -84,20 +82,33 @@ def partitionChunks(tileInfo, world):
 
 def partitionTiles(tileInfo, world):
     """
-    owner rank of every tile.  The ranks form a grid of pr x pc rectangular blocks of tiles
-    (pr * pc = world, ranks numbered row-major over the blocks): a rank then has remote upper or
-    left neighbours only along the top row and left column of its block, and only those tiles
-    have to wait for the other ranks before their stitch tables can be made.  Among the grids
-    that fit, the one with the smallest largest block cost wins, fewer boundary tiles on ties.
-    Without a fitting grid (or with one block per rank row anyway) the row-major list is cut
-    into contiguous chunks.  The reference deals tiles round-robin over its workers
-    (tiling.py:892-893); which worker segments a tile does not change the result.
+    owner rank of every tile.  The tile rows are cut into pr bands and every band, its tiles taken
+    column by column, into pc contiguous pieces of as equal a segmentation cost as possible
+    (pr * pc = world, ranks numbered band after band): a rank owns a block of whole tile columns
+    plus at most a partial column at either end, so that it has remote upper or left neighbours
+    only along the rim of its block, and only those tiles have to wait for another rank's
+    strips before their stitch tables can be made.  Among the (pr, pc) that fit, the one with
+    the smallest largest cost wins, fewer rim tiles on ties; contiguous chunks of the row-major
+    list (pr = world bands cannot be formed, say) are the fall-back.  The reference deals tiles
+    round-robin over its workers (tiling.py:892-893); which worker segments a tile does not
+    change the result.
     """
     (nrows, ncols) = (tileInfo.nrows, tileInfo.ncols)
     if world <= 1:
         return dict((cr, 0) for cr in tileInfo.tiles)
-    heights = [tileInfo.tiles[(0, r)][3] for r in range(nrows)]
-    widths = [tileInfo.tiles[(c, 0)][2] for c in range(ncols)]
+    key = (world, tuple(sorted(tileInfo.tiles.items())))
+    if key not in _partitionCache:
+        _partitionCache.clear()
+        _partitionCache[key] = _partitionTiles(tileInfo, world)
+    return dict(_partitionCache[key])
+
+
+_partitionCache = {}
+
+
+def _partitionTiles(tileInfo, world):
+    (nrows, ncols) = (tileInfo.nrows, tileInfo.ncols)
+    rowCost = [sum(_tileCost(tileInfo.tiles[(c, r)]) for c in range(ncols)) for r in range(nrows)]
     best = None
     for pr in range(1, world + 1):
         if world % pr:
@@ -105,27 +116,31 @@ def partitionTiles(tileInfo, world):
         pc = world // pr
         if pr > nrows or pc > ncols:
             continue
-        rg = _splitBalanced([h + 1e-9 for h in heights], pr)
-        cg = _splitBalanced([w + 1e-9 for w in widths], pc)
+        rg = _splitBalanced(rowCost, pr)
+        owner = {}
+        for band in range(pr):
+            rows = [r for r in range(nrows) if rg[r] == band]
+            cells = [(c, r) for c in range(ncols) for r in rows]          # column by column
+            if len(cells) < pc:
+                owner = None
+                break
+            groups = _splitBalanced([_tileCost(tileInfo.tiles[cr]) for cr in cells], pc)
+            for (cr, g) in zip(cells, groups):
+                owner[cr] = band * pc + g
+        if owner is None:
+            continue
         cost = numpy.zeros(world)
-        boundary = 0
+        rim = 0
         for ((c, r), t) in tileInfo.tiles.items():
-            cost[rg[r] * pc + cg[c]] += _tileCost(t)
-            if (r > 0 and rg[r - 1] != rg[r]) or (c > 0 and cg[c - 1] != cg[c]):
-                boundary += 1
-        key = (round(float(cost.max()), 6), boundary)
+            cost[owner[(c, r)]] += _tileCost(t)
+            if (r > 0 and owner[(c, r - 1)] != owner[(c, r)]) or (c > 0 and owner[(c - 1, r)] != owner[(c, r)]):
+                rim += 1
+        key = (round(float(cost.max()), 6), rim)
         if best is None or key < best[0]:
-            best = (key, rg, cg, pc)
-    chunks = partitionChunks(tileInfo, world)
+            best = (key, owner)
     if best is None:
-        return chunks
-    (key, rg, cg, pc) = best
-    chunkCost = numpy.zeros(world)
-    for (cr, g) in chunks.items():
-        chunkCost[g] += _tileCost(tileInfo.tiles[cr])
-    if chunkCost.max() < 0.8 * key[0]:
-        return chunks           # the blocks are much less even than the chunks would be
-    return dict(((c, r), rg[r] * pc + cg[c]) for (c, r) in tileInfo.tiles)
+        return partitionChunks(tileInfo, world)
+    return best[1]
 
 
 class TileTable(object):

@@ -9,6 +9,6 @@ print('value %.0f  ms/step %.2f  e2e %.0f (%.1f ms)  parity_vs_one_rank %s  pari
 if line.get('one_rank'):
     print(line['one_rank'])
 for (i, r) in enumerate(line.get('per_rank') or []):
-    print('rank', i, r['tiles'], 'tiles', r['tile_mpix'], 'Mpix')
+    print('rank', i, r['tiles'], 'tiles', r['tile_mpix'], 'Mpix', r.get('step_wall_ms'))
     print('   resident', r['resident'])
     print('   e2e     ', r['e2e'])
