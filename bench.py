@@ -63,6 +63,16 @@ RESIDENT_WORKERS = int(os.environ.get('BENCH_RESIDENT_WORKERS', '2'))   # 0: seg
 def algorithmic_bytes_per_pixel(kernel, nB):
     table = {
         'k_assign': 2 * nB + 4,            # read the bands, write the int32 cluster
+        'k_assign_grid': 2 * nB + 4,
+        'k_pixel_pass': 2 * nB + 8,        # bands once, label read (pending relabel folded in) + written
+        'k_apply_lut_extents': 8,          # label read + final label written (extent tables are per segment)
+        'k_ccl_flatten_count': 8,
+        # the region-merge kernels only touch segment records (32 B each), a few bytes per pixel;
+        # they are charged the whole "eliminate small segments" figure of SURVEY 8(d) -- bands
+        # once, labels read + written -- because that stage is what they dominate
+        'k_merge_wide': 2 * nB + 8,
+        'k_merge_lean': 2 * nB + 8,
+        'k_merge_tail': 2 * nB + 8,
         'k_ccl_local': 8,                  # read cluster, write root label
         'k_ccl_flatten': 8,
         'k_gather_ids': 8,
@@ -171,6 +181,14 @@ class ClockSampler(object):
             pynvml.nvmlInit()
             self.nvml = pynvml
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            # the first call of every query is slow (tens of ms) and holds up CUDA calls of this
+            # process meanwhile: make them here, before the timed region starts
+            n = pynvml
+            n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            (n.nvmlDeviceGetCurrentClocksEventReasons if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons')
+                else n.nvmlDeviceGetCurrentClocksThrottleReasons)(self.handle)
+            n.nvmlDeviceGetPowerUsage(self.handle)
+            n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
             self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
         except Exception:
@@ -599,6 +617,7 @@ def run_ours(args, wl):
     # per-kernel durations for the roofline: the same steps once more on ONE stream with an event
     # pair around every launch (with several worker streams an event pair would also span the
     # other streams' kernels)
+    step_resident(profile=True)       # (the first single-stream pass sizes its own scratch: not timed)
     (msProfiled, lastProf) = timed(resident_profiled, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     if os.environ.get('SSG_TIMELINE') and rank == 0 and lastE2E[0].timeline:
@@ -717,7 +736,7 @@ def run_ours(args, wl):
             key=lambda kv: -kv[1][1])[:24])
         # secondary rooflines of the two bandwidth kernels the north star names
         extra = {}
-        for name in ('k_assign', 'k_ccl_local'):
+        for name in ('k_assign', 'k_assign_grid', 'k_ccl_local', 'k_pixel_pass', 'k_gather_ids', 'k_apply_lut_extents'):
             if name in kernelAgg and kernelAgg[name][1] > 0:
                 b = algorithmic_bytes_per_pixel(name, nB)
                 gbs = b * tilePixels * args.steps / (kernelAgg[name][1] / 1e3) / 1e9
@@ -795,6 +814,13 @@ def run_ours(args, wl):
             'one_rank': vsOneRank,
             'segments_per_scene': int(lastRes[1]),
             'stage_ms_per_step': dict((k, round(v, 3)) for (k, v) in lastProf[0].stageMs.items()),
+            # the stages against the HBM roofline with SURVEY 8(d)'s per-pixel figures: assign reads the
+            # bands and writes a label, clump reads and writes a label, the two eliminate stages read
+            # the bands once and read + write the labels
+            'roofline_stages': dict((k, {'bytes_per_pixel': b, 'achieved': b * tilePixels / (lastProf[0].stageMs[k] / 1e3) / 1e9,
+                    'frac': b * tilePixels / (lastProf[0].stageMs[k] / 1e3) / 1e9 / peak})
+                for (k, b) in (('assign', 2 * nB + 4), ('clump', 8), ('single', 2 * nB + 8), ('small', 2 * nB + 8))
+                if lastProf[0].stageMs.get(k)),
             'per_rank': perRank,
             'host_ms_last_step': {
                 'resident': dict((k, round(v['total'] * 1e3, 2)) for (k, v) in
