@@ -1,7 +1,7 @@
 """Turn ncu csv exports (launch list + --page raw) into the markdown summaries kept in profiles/.
 
     python tools/summarize_ncu.py launches <launches.csv> [first-kernel-regex]   > profiles/xxx_launches.md
-    python tools/summarize_ncu.py raw <raw.csv>                                  > profiles/xxx_full.md
+    python tools/summarize_ncu.py raw <raw.csv> [last]                           > profiles/xxx_full.md
 """
 import csv
 import re
@@ -55,14 +55,20 @@ WANT = [
 ]
 
 
-def raw(path):
+def raw(path, last=False):
     rows = list(csv.reader(open(path)))
     (hdr, units) = (rows[0], rows[1])
     ci = dict((h, i) for (i, h) in enumerate(hdr))
     cols = [(h, n) for (h, n) in WANT if h in ci]
     print('| kernel | ' + ' | '.join(n for (_, n) in cols) + ' |')
     print('|---|' + '---|' * len(cols))
-    for r in rows[2:]:
+    body = rows[2:]
+    if last:       # several passes captured: keep the last launch of every kernel (warm caches, sized scratch)
+        seen = OrderedDict()
+        for r in body:
+            seen[(r[ci['Kernel Name']], r[ci['launch__grid_size']] if 'launch__grid_size' in ci else '')] = r
+        body = list(seen.values())
+    for r in body:
         vals = []
         for (h, _) in cols:
             v = r[ci[h]]
@@ -80,4 +86,4 @@ if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
-        raw(sys.argv[2])
+        raw(sys.argv[2], last=len(sys.argv) > 3 and sys.argv[3] == 'last')
