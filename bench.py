@@ -90,15 +90,17 @@ def algorithmic_bytes_per_pixel(kernel, nB):
     return table.get(kernel)
 
 
-# DRAM bytes per pixel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture on
-# a 4096 x 4096 x 4 tile, profiles/r1_tile4096_ncu_full.md, divided by the tile's pixels): scaled by
+# DRAM bytes per pixel (dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full` captures on
+# a 4096 x 4096 x 4 tile, profiles/r2_tile4096_ncu_full.md, divided by the tile's pixels): scaled by
 # the pixels one launch processes it gives `roofline.traffic`
 NCU_DRAM_BYTES_PER_PIXEL = {
-    'k_small_persistent': (130.1e6 + 40.0e6) / 4096 ** 2,
-    'k_assign': (134.5e6 + 40.9e6) / 4096 ** 2,
-    'k_ccl_local': (67.2e6 + 24.8e6) / 4096 ** 2,
-    'k_band_sums': (220.0e6 + 9.5e6) / 4096 ** 2,
-    'k_gather_ids': (122.8e6 + 31.9e6) / 4096 ** 2,
+    'k_merge_wide': (96.4e6 + 20.1e6) / 4096 ** 2,
+    'k_merge_lean': (52.9e6 + 2.1e6) / 4096 ** 2,
+    'k_assign_grid': (135.4e6 + 41.5e6) / 4096 ** 2,
+    'k_ccl_local': (67.2e6 + 26.8e6) / 4096 ** 2,
+    'k_pixel_pass': (219.6e6 + 63.2e6) / 4096 ** 2,
+    'k_gather_ids': (122.7e6 + 35.3e6) / 4096 ** 2,
+    'k_ccl_flatten_count': (67.1e6 + 6.5e6) / 4096 ** 2,
 }
 
 
@@ -725,7 +727,7 @@ def run_ours(args, wl):
             roof['bytes_per_pixel'] = bpp
             if domName in NCU_DRAM_BYTES_PER_PIXEL:
                 roof['traffic'] = NCU_DRAM_BYTES_PER_PIXEL[domName] * tilePixels / max(1.0, launchesPerStep)
-                roof['traffic_source'] = ('ncu --set full on a 4096x4096x4 tile (profiles/r1_tile4096_ncu_full.md): '
+                roof['traffic_source'] = ('ncu --set full on a 4096x4096x4 tile (profiles/r2_tile4096_ncu_full.md): '
                     '%.1f DRAM bytes per pixel, scaled to the mean tile of a launch' % NCU_DRAM_BYTES_PER_PIXEL[domName])
             roof['avg_launch_ms'] = avgMs
             roof['launches_per_step'] = launchesPerStep
