@@ -142,6 +142,9 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
+            if lib.ssg_abi_version() != ABI_VERSION:
+                raise ShepsegB200Error('libshepseg_b200.so has ABI version %d, this binding needs %d: '
+                    'rebuild it (make -C pyshepseg_b200/csrc)' % (lib.ssg_abi_version(), ABI_VERSION))
             _lib = lib
     return _lib
 
