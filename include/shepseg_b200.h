@@ -290,6 +290,14 @@ int ssg_apply_rel_lut_device(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysiz
                              const uint32_t *crossLabelsHost, const uint32_t *crossIdsHost,
                              int64_t top, int64_t bottom, int64_t left, int64_t right,
                              uint32_t *outDev, int64_t outStride, uint64_t *histDev, int64_t histLen);
+/* Overviews of a window that is in device memory (TilingSegmenter.writeOverviews,
+ * tiling.py:1360-1383): for every level L the sub-sampled window arr[L/2::L, L/2::L], all levels
+ * packed one after the other (each row-major) into outHost; startsOut (nLevels + 1) receives the
+ * element offset of every level and the total.  Level l has len(range(L/2, wRows, L)) rows and
+ * len(range(L/2, wCols, L)) columns.  Synchronous. */
+int ssg_window_overviews(ssg_ctx *ctx, const uint32_t *winDev, int64_t wRows, int64_t wCols,
+                         int64_t winStride, int nLevels, const int32_t *levels, uint32_t *outHost,
+                         int64_t outCapacity, int64_t *startsOut);
 
 /* ---- plain device memory helpers (so the Python side needs nothing but ctypes) -------- */
 int ssg_dev_alloc(ssg_ctx *ctx, size_t bytes, void **out);

@@ -98,6 +98,7 @@ SIGNATURES = {
         _vp, _i64]),
     'ssg_apply_rel_lut_device': (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _u32, _u32, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
         _vp, _i64, _vp, _i64]),
+    'ssg_window_overviews': (_i, [_vp, _vp, _i64, _i64, _i64, _i, _vp, _vp, _i64, _vp]),
     'ssg_dev_alloc': (_i, [_vp, _sz, _c.POINTER(_vp)]),
     'ssg_dev_free': (_i, [_vp, _vp]),
     'ssg_memcpy_h2d': (_i, [_vp, _vp, _vp, _sz]),

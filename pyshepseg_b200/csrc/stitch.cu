@@ -542,3 +542,67 @@ static int apply_lut_window(ssg_ctx *ctx, const uint32_t *tileDev, int64_t ysize
     }
     return SSG_OK;
 }
+
+// ---- overviews of a written window (TilingSegmenter.writeOverviews, tiling.py:1360-1383) ------
+// For every overview level L the reference keeps every L-th pixel of the window in both
+// directions, starting L/2 in from the window's top-left corner: sub = arr[L//2::L, L//2::L].
+// All levels of a window are cut out in one launch into one packed buffer (level after level,
+// each row-major), which the caller copies to the host in one piece.
+#define SSG_MAX_OVERVIEW_LEVELS 16
+struct OverviewPlan {
+    int n;
+    int level[SSG_MAX_OVERVIEW_LEVELS];
+    long long rows[SSG_MAX_OVERVIEW_LEVELS], cols[SSG_MAX_OVERVIEW_LEVELS];
+    long long start[SSG_MAX_OVERVIEW_LEVELS + 1];       // element offset of every level in the packed buffer
+};
+
+__global__ void __launch_bounds__(256)
+k_window_overviews(const unsigned *__restrict__ win, int64_t winStride, OverviewPlan plan, unsigned *out)
+{
+    const long long total = plan.start[plan.n];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int l = 0;
+        while (l + 1 < plan.n && i >= plan.start[l + 1]) l++;
+        const long long j = i - plan.start[l];
+        const long long r = j / plan.cols[l], c = j - r * plan.cols[l];
+        const long long L = plan.level[l], o = L / 2;
+        out[i] = win[(o + r * L) * winStride + (o + c * L)];
+    }
+}
+
+extern "C" int ssg_window_overviews(ssg_ctx *ctx, const uint32_t *winDev, int64_t wRows, int64_t wCols,
+                                    int64_t winStride, int nLevels, const int32_t *levels, uint32_t *outHost,
+                                    int64_t outCapacity, int64_t *startsOut)
+{
+    if (!ctx) return SSG_ERR_ARG;
+    ctx->err.clear();
+    SSG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!winDev || !levels || !outHost || !startsOut || nLevels < 1 || nLevels > SSG_MAX_OVERVIEW_LEVELS || wRows < 0 || wCols < 0)
+        SSG_FAIL(ctx, SSG_ERR_ARG, "bad argument (1..%d overview levels)", SSG_MAX_OVERVIEW_LEVELS);
+    OverviewPlan plan = {};
+    plan.n = nLevels;
+    for (int l = 0; l < nLevels; l++) {
+        if (levels[l] < 1) SSG_FAIL(ctx, SSG_ERR_ARG, "overview level %d", levels[l]);
+        const long long L = levels[l], o = L / 2;
+        plan.level[l] = levels[l];
+        plan.rows[l] = wRows > o ? (wRows - o + L - 1) / L : 0;      // len(range(o, wRows, L))
+        plan.cols[l] = wCols > o ? (wCols - o + L - 1) / L : 0;
+        plan.start[l + 1] = plan.start[l] + plan.rows[l] * plan.cols[l];
+        startsOut[l] = plan.start[l];
+    }
+    startsOut[nLevels] = plan.start[nLevels];
+    const long long total = plan.start[nLevels];
+    if (total > outCapacity) SSG_FAIL(ctx, SSG_ERR_ARG, "overview buffer of %lld elements, %lld needed", (long long)outCapacity, total);
+    if (total == 0) return SSG_OK;
+    SSG_TRY(ssg_reserve(ctx, ctx->stitch2, (size_t)total * sizeof(unsigned)));
+    unsigned *out = bufp<unsigned>(ctx->stitch2);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)ctx->numSMs * 16) blocks = (int64_t)ctx->numSMs * 16;
+    SSG_PROF_BEGIN(ctx, "k_window_overviews");
+    k_window_overviews<<<(unsigned)blocks, 256, 0, ctx->stream>>>(winDev, winStride, plan, out);
+    SSG_LAUNCHED(ctx);
+    SSG_CUDA(ctx, cudaMemcpyAsync(outHost, out, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    SSG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SSG_OK;
+}
+

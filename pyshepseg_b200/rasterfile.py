@@ -274,6 +274,12 @@ class RasterSink(object):
         pass
 
     def writeOverviews(self, arr, xoff, yoff):
+        """All overview levels of the window arr written at (xoff, yoff) (tiling.py:1360-1383)."""
+        for (j, lvl) in enumerate(getattr(self, 'levels', None) or []):
+            self.writeOverviewLevel(j, lvl, arr[lvl // 2::lvl, lvl // 2::lvl], xoff // lvl, yoff // lvl)
+
+    def writeOverviewLevel(self, j, lvl, sub, xs, ys):
+        """sub = the window sub-sampled for level number j (= lvl), to go at (xs, ys) of that level."""
         pass
 
     def close(self):
@@ -305,13 +311,10 @@ class MemorySink(RasterSink):
         self.overviews = dict((lvl, numpy.zeros((-(-ysize // lvl), -(-xsize // lvl)), dtype=dtype))
             for lvl in self.levels)
 
-    def writeOverviews(self, arr, xoff, yoff):
-        for lvl in self.levels:
-            ov = self.overviews[lvl]
-            sub = arr[lvl // 2::lvl, lvl // 2::lvl]
-            (xs, ys) = (xoff // lvl, yoff // lvl)
-            sub = sub[:ov.shape[0] - ys, :ov.shape[1] - xs]
-            ov[ys:ys + sub.shape[0], xs:xs + sub.shape[1]] = sub
+    def writeOverviewLevel(self, j, lvl, sub, xs, ys):
+        ov = self.overviews[lvl]
+        sub = sub[:ov.shape[0] - ys, :ov.shape[1] - xs]      # (do not go off the edges)
+        ov[ys:ys + sub.shape[0], xs:xs + sub.shape[1]] = sub
 
     def write(self, arr, xoff, yoff):
         self.array[yoff:yoff + arr.shape[0], xoff:xoff + arr.shape[1]] = arr
@@ -452,13 +455,10 @@ class GdalSink(RasterSink):      # pragma: no cover - exercised only where GDAL 
     def write(self, arr, xoff, yoff):
         self.band.WriteArray(arr, xoff, yoff)
 
-    def writeOverviews(self, arr, xoff, yoff):
-        for (j, lvl) in enumerate(self.levels):
-            ov = self.band.GetOverview(j)
-            sub = arr[lvl // 2::lvl, lvl // 2::lvl]
-            (xs, ys) = (xoff // lvl, yoff // lvl)
-            sub = sub[:ov.YSize - ys, :ov.XSize - xs]
-            ov.WriteArray(sub, xs, ys)
+    def writeOverviewLevel(self, j, lvl, sub, xs, ys):
+        ov = self.band.GetOverview(j)
+        sub = sub[:ov.YSize - ys, :ov.XSize - xs]
+        ov.WriteArray(numpy.ascontiguousarray(sub), xs, ys)
 
     def setNoData(self, value):
         self.band.SetNoDataValue(value)
@@ -497,7 +497,7 @@ def createRaster(outfile, xsize, ysize, driver, options, source=None):
     if isinstance(outfile, RasterSink):
         return outfile
     if driver == 'MEM' or outfile is None:
-        return MemorySink(xsize, ysize)
+        return MemorySink(xsize, ysize, levels=overviewLevels(xsize, ysize))
     if driver == 'NPY':
         return NpySink(outfile, xsize, ysize)
     if _gdal is not None:

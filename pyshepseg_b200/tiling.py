@@ -300,7 +300,15 @@ class _Slot(object):
         self.devStage = None     # (cap, ptr): tile image gathered from a DeviceRaster
         self.window = None       # PinnedArray staging of one trimmed output window
         self.winDev = None       # (cap, ptr)
+        self.ovBuf = None        # PinnedArray: the overview levels of one window, packed
         self.lock = threading.Lock()
+
+    def overviewsFor(self, nItems):
+        if self.ovBuf is None or self.ovBuf.array.size < nItems:
+            if self.ovBuf is not None:
+                self.ovBuf.free()
+            self.ovBuf = _lib.PinnedArray((max(nItems, 1),), numpy.uint32)
+        return self.ovBuf.array
 
     def pinnedFor(self, nItems, dtype):
         nbytes = nItems * numpy.dtype(dtype).itemsize
@@ -333,6 +341,8 @@ class _Slot(object):
             self.pinned.free()
         if self.window is not None:
             self.window.free()
+        if self.ovBuf is not None:
+            self.ovBuf.free()
         if self.devStage is not None:
             self.ctx.dev_free(self.devStage[1])
         if self.winDev is not None:
@@ -776,6 +786,19 @@ class TiledSegmenter(object):
         else:
             (window, winDev) = slot.windowFor(wr * wc)
             kernel(winDev, wc)
+            levels = [int(v) for v in (getattr(sink, 'levels', None) or [])]
+            if levels:
+                # the overview levels of the window, cut out on the device (tiling.py:1360-1383)
+                shapes = [(len(range(lvl // 2, wr, lvl)), len(range(lvl // 2, wc, lvl))) for lvl in levels]
+                total = sum(r * c for (r, c) in shapes)
+                packed = slot.overviewsFor(total)
+                starts = numpy.zeros(len(levels) + 1, dtype=numpy.int64)
+                ctx.call('ssg_window_overviews', winDev, wr, wc, wc, len(levels),
+                    _lib.ptr(numpy.array(levels, dtype=numpy.int32)), _lib.ptr(packed), packed.size, _lib.ptr(starts))
+                for (j, (lvl, (r, c))) in enumerate(zip(levels, shapes)):
+                    sink.writeOverviewLevel(j, lvl, packed[starts[j]:starts[j] + r * c].reshape(r, c),
+                        xout // lvl, yout // lvl)
+                self.d2hBytes += total * 4
             arr = getattr(sink, 'array', None)
             if (type(sink) is rasterfile.MemorySink and isinstance(arr, numpy.ndarray) and
                     arr.flags.c_contiguous and arr.dtype == numpy.uint32):
@@ -794,7 +817,8 @@ class TiledSegmenter(object):
                 out = window[:wr * wc].reshape(wr, wc)
                 ctx.call('ssg_memcpy_d2h', _lib.ptr(out), winDev, wr * wc * 4)
                 sink.write(out, xout, yout)
-                sink.writeOverviews(out, xout, yout)
+                if not levels:
+                    sink.writeOverviews(out, xout, yout)
             self.d2hBytes += wr * wc * 4
 
     def stitchOne(self, slot, pool, tile, offset, sink, hist, deferred=None):

@@ -168,3 +168,39 @@ def test_unsupported_raster_type_is_a_tiling_error(tiling):
     with pytest.raises(tiling.PyShepSegTilingError, match='not supported'):
         tiling.doTiledShepherdSegmentation(rasterfile.MemoryRaster(img), None, tileSize=32, overlapSize=8,
             kmeansObj=km, outputDriver='MEM')
+
+
+@pytest.mark.parametrize('workers', [0, 2])
+def test_overviews_cut_on_the_device(tiling, workers):
+    """The overview levels of every written window as TilingSegmenter.writeOverviews makes them
+    (tiling.py:1360-1383: arr[L//2::L, L//2::L] of the trimmed window at (xOff//L, yOff//L)),
+    cut out by ssg_window_overviews; the default MEM output carries the reference's level list."""
+    c = goldenutil.load('tiled_700x900')
+    m = c['meta']
+    img = c['img']
+    (nB, nR, nC) = img.shape
+    levels = [2, 4, 8, 5]
+    sink = rasterfile.MemorySink(nC, nR, levels=levels)
+    cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=workers) \
+        if workers else None
+    res = tiling.doTiledShepherdSegmentation(rasterfile.MemoryRaster(img, nodata=m['imgNullVal']), sink,
+        tileSize=m['tileSize'], overlapSize=m['overlapSize'], minSegmentSize=m['minSegmentSize'],
+        numClusters=m['numClusters'], imgNullVal=m['imgNullVal'], fourConnected=m['fourConnected'],
+        kmeansObj=goldenutil.Centres(c['centres']), simpleTileRecode=m['simpleTileRecode'], returnGDALDS=True,
+        concurrencyCfg=cfg)
+    same(sink.array, c['mosaic'], 'mosaic')
+    ti = tiling.getTilesForFile((nC, nR), m['tileSize'], m['overlapSize'])
+    for lvl in levels:
+        want = numpy.zeros((-(-nR // lvl), -(-nC // lvl)), dtype=numpy.uint32)
+        for ((col, row), (x, y, xs, ys)) in sorted(ti.tiles.items(), key=lambda kv: (kv[0][1], kv[0][0])):
+            (top, bottom, left, right) = tiling.tileMargins(ti, col, row, xs, ys, m['overlapSize'])
+            arr = c['mosaic'][y + top:y + bottom, x + left:x + right]
+            sub = arr[lvl // 2::lvl, lvl // 2::lvl]
+            (xo, yo) = ((x + left) // lvl, (y + top) // lvl)
+            sub = sub[:want.shape[0] - yo, :want.shape[1] - xo]
+            want[yo:yo + sub.shape[0], xo:xo + sub.shape[1]] = sub
+        same(sink.overviews[lvl], want, 'overview level %d' % lvl)
+    # the output the function creates itself has the reference's levels (none for a raster this small)
+    res2 = run_tiled(tiling, img, goldenutil.Centres(c['centres']), m)
+    assert list(res2.outDs.levels) == rasterfile.overviewLevels(nC, nR)
+
