@@ -68,3 +68,63 @@ def test_two_ranks_equal_reference_mosaic(name):
     assert int(maxSegId) == c['meta']['maxSegId']
     assert numpy.array_equal(mosaic, c['mosaic'])
     assert numpy.array_equal(numpy.asarray(hist), c['hist'])
+
+
+def _rank_main_api(rank, world, port, name, resq):
+    """the same through the public function: every rank hands doTiledShepherdSegmentation the
+    WINDOW of the raster its tiles cover (row and column offsets) and a sink of that window"""
+    import torch.distributed as dist
+    from pyshepseg_b200 import tiling, distributed, rasterfile
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    try:
+        c = goldenutil.load(name)
+        m = c['meta']
+        img = c['img']
+        (nB, nR, nC) = img.shape
+        ti = tiling.getTilesForFile((nC, nR), m['tileSize'], m['overlapSize'])
+        owner = distributed.partitionTiles(ti, world)
+        mine = [(cr, t) for (cr, t) in ti.tiles.items() if owner[cr] == rank]
+        (x0, x1) = (min(t[0] for (cr, t) in mine), max(t[0] + t[2] for (cr, t) in mine))
+        (y0, y1) = (min(t[1] for (cr, t) in mine), max(t[1] + t[3] for (cr, t) in mine))
+        src = rasterfile.MemoryRaster(numpy.ascontiguousarray(img[:, y0:y1, x0:x1]), nodata=m['imgNullVal'],
+            yoff=y0, fullYsize=nR, xoff=x0, fullXsize=nC)
+        sink = rasterfile.MemorySink(x1 - x0, y1 - y0, yoff=y0, xoff=x0)
+        cfg = tiling.SegmentationConcurrencyConfig(concurrencyType=tiling.CONC_THREADS, numWorkers=1 + rank)
+        cfg.comm = distributed.TorchComm()
+        res = tiling.doTiledShepherdSegmentation(src, sink, tileSize=m['tileSize'], overlapSize=m['overlapSize'],
+            minSegmentSize=m['minSegmentSize'], numClusters=m['numClusters'], imgNullVal=m['imgNullVal'],
+            fourConnected=m['fourConnected'], kmeansObj=goldenutil.Centres(c['centres']),
+            simpleTileRecode=m['simpleTileRecode'], returnGDALDS=True, concurrencyCfg=cfg)
+        full = numpy.zeros((nR, nC), dtype=numpy.int64)
+        for ((col, row), (x, y, xs, ys)) in mine:
+            (top, bottom, left, right) = tiling.tileMargins(ti, col, row, xs, ys, m['overlapSize'])
+            full[y + top:y + bottom, x + left:x + right] = \
+                sink.array[y + top - y0:y + bottom - y0, x + left - x0:x + right - x0]
+        total = cfg.comm.allreduceSum(full)     # windows are disjoint
+        if rank == 0:
+            resq.put((int(res.maxSegId), total.astype(numpy.uint32), numpy.asarray(res.outDs.hist),
+                res.outDs.metadata.get('STATISTICS_MAXIMUM'), res.gpuLaunches))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('name', ['tiled_700x900', 'tiled_640_5x5_8conn'])
+def test_two_ranks_through_the_public_function(name):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    resq = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_rank_main_api, args=(r, 2, port, name, resq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    (maxSegId, mosaic, hist, statMax, launches) = resq.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    c = goldenutil.load(name)
+    assert launches > 0
+    assert maxSegId == c['meta']['maxSegId']
+    assert numpy.array_equal(mosaic, c['mosaic'])
+    assert numpy.array_equal(hist, c['hist'])
+    assert statMax == repr(c['meta']['maxSegId'])
+
