@@ -2,7 +2,7 @@
 bench.py -- Mpixels/s of the full Shepherd segmentation (assign + clump + eliminate + stitch)
 on B200, next to the CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4_40000]
 
 A step is one pass of the hot path over one synthetic raster: the workload named by
 BASELINE.json configs[1], a Sentinel-2-like 10980 x 10980 x 4 uint16 raster segmented by
@@ -18,10 +18,19 @@ Two numbers per run:
          memory, copies inside the timed region (the public path of doTiledShepherdSegmentation
          with two segmentation workers overlapping copies and kernels).
 
-With --gpus N (launched by torchrun, one rank per GPU) every rank segments its own scene of
-the same shape (weak scaling; tiles of different scenes are independent, so the data path has
-no collective); NCCL broadcasts the cluster centres from rank 0 and all-gathers every scene's
-segment count per step, from which each scene's global id base follows.
+With --gpus N (launched by torchrun, one rank per GPU) the raster is ONE mosaic of N such scenes
+(weak scaling), its tiles dealt over the ranks (pyshepseg_b200.distributed): every rank holds the
+window of the raster its tiles cover, segments them, and the ranks stitch the mosaic with global
+ids -- overlap strips device to device over NCCL, two or three small all-gathers, no data-path
+collective; NCCL also broadcasts the cluster centres from rank 0.  After the timed regions the
+N-rank mosaic is compared with rank 0 segmenting the same raster alone (parity_vs_one_rank).
+--workload c4_40000 is BASELINE config 4 instead: one 40000 x 40000 x 4 mosaic whatever N
+(strong scaling, 144 tiles).
+
+Also in the line: roofline (dominant kernel by event-timed share, algorithmic bytes against the
+measured HBM peak, ncu DRAM traffic), roofline_other / roofline_stages, kernels (event pair per
+launch on one stream), cpu_baseline (numba reference) and cpu_baseline_port, clocks, and
+parity_vs_oracle: the e2e mosaic of the last timed step against the CPU oracle on the same raster.
 
 --impl reference times the reference itself on the host cores: the UNMODIFIED pyshepseg 2.0.3
 (installed from /root/reference into the git-ignored baseline/_ref/, numba + scikit-learn) runs

@@ -8,22 +8,30 @@ carrying the running maxSegId and the recoded overlap strips of the finished nei
 three small exchanges when the tiles live on different ranks:
 
   strips   the LOCAL labels of an upper / left neighbour under a tile's overlap, when that
-           neighbour lives on another rank (device-to-device send/recv, NCCL over NVLink);
-  counts   one integer per tile, the highest rank among its self-numbered segments inside its
+           neighbour lives on another rank (device-to-device send/recv, NCCL over NVLink).  A
+           rank segments the tiles that feed other ranks first, so the exchange can run while
+           the rest of its tiles are still in work (feedPlan / exchangeStrips);
+  steps    one integer per tile, the highest rank among its self-numbered segments inside its
            trimmed window: the id offset of tile t is the sum over the tiles before it (one
            all-gather).  That is what the reference's "maxSegId = max(maxSegId, trimmed.max())"
            (tiling.py:1042-1043) amounts to unless a window holds an inherited id above the
            running maximum; the recurrence is checked on every tile after the resolve and the
            ranks fall back to the sequential order over all tables if it fails anywhere, so the
-           result is the reference's in every case;
-  tables   the per-segment tables (rank, flags, votes) of the tiles whose final ids a tile on
-           another rank has to look up: a crossing segment takes the final id of the neighbour
-           segment it overlaps most (recodeSharedSegments, tiling.py:1128-1203), and that id may
-           in turn be inherited from the neighbour's neighbour.  Look-ups are lazy and per
-           entry, so no rank replays another rank's tiles.
+           result is the reference's in every case.  Until the offsets are known ids are handled
+           SYMBOLICALLY, as (index of the tile that numbered the segment) << 32 | rank: such
+           values order and compare like the final ids, so every vote can be taken before a
+           single offset exists, and offset + rank is left to the device at the very end;
+  look-ups the final ids of single labels of a tile on another rank: a crossing segment takes
+           the final id of the neighbour segment it overlaps most (recodeSharedSegments,
+           tiling.py:1128-1203), and that id may in turn be inherited from the neighbour's
+           neighbour.  The owner of a tile answers what it has settled; requests travel with the
+           steps' all-gather, so a mosaic costs two or three collectives.  No rank replays
+           another rank's tiles and no tables are shipped (except in the fall-back).
 
-Everything here is host logic on numpy arrays; the device work is behind the `ops` object the
-caller hands in (tiling.TiledSegmenter for the GPU, plain numpy in the CPU tests).
+Only the crossing segments of a tile (a few thousand) are ever handled here; nothing of a tile's
+full length is computed on the host.  Everything in this module is host logic on numpy arrays;
+the device work is behind the `ops` object the caller hands in (tiling.TiledSegmenter for the
+GPU, plain numpy in the CPU tests).
 """
 import io
 
