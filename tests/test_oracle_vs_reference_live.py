@@ -131,3 +131,80 @@ def test_oracle_stitch_equals_reference_tiled_run(tmp_path):
     (mosaic, maxSegId, hist) = oracle.stitchTiles(segs, ti, nC, nR, c['overlap'])
     assert maxSegId == int(ref['maxSegId'])
     assert numpy.array_equal(mosaic, ref['mosaic'])
+
+
+STATS_RUNNER = r'''
+import json, os, sys
+import numpy
+sys.path.insert(0, %(golden)r)
+import fake_gdal
+gdal = fake_gdal.install()
+class _SR(object):
+    def __init__(self, wkt=''):
+        self.wkt = wkt
+    def IsSame(self, other):
+        return self.wkt == other.wkt
+sys.modules['osgeo.osr'].SpatialReference = _SR
+sys.modules['osgeo.osr'].UseExceptions = lambda: None
+sys.path.insert(0, %(ref)r)
+from pyshepseg import tilingstats
+spec = json.load(open(sys.argv[1]))
+d = numpy.load(spec['npz'])
+(seg, img) = (d['seg'], d['img'])
+fake_gdal.put_image('img', img[None], nodata=spec['imgNull'])
+segds = fake_gdal.put_image('seg', seg[None].copy())
+rat = segds.GetRasterBand(1).GetDefaultRAT()
+hist = numpy.bincount(seg.ravel(), minlength=int(seg.max()) + 1).astype(numpy.float64)
+hist[0] = 0
+rat.SetRowCount(len(hist))
+rat.CreateColumn('Histogram', gdal.GFT_Real, gdal.GFU_PixelCount)
+rat.WriteArray(hist, 0)
+sel = [tuple(s) for s in spec['selection']]
+tilingstats.calcPerSegmentStatsTiled('img', 1, 'seg', sel, missingStatsValue=spec['missing'])
+numpy.savez(spec['out'], **dict((c[0], numpy.asarray(c[3])) for c in rat.cols if c[0] != 'Histogram'))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'pyshepseg')),
+    reason='the reference checkout is not on this machine')
+@pytest.mark.parametrize('dtype,imgNull,seed', [(numpy.uint16, None, 201), (numpy.int16, -5, 202), (numpy.uint32, 0, 203)])
+def test_stats_oracle_equals_reference_on_fresh_cases(tmp_path, dtype, imgNull, seed):
+    """the per-segment statistics: the unmodified tilingstats.calcPerSegmentStatsTiled (through the
+    GDAL stand-in, in a subprocess) against oracle/stats_oracle.py on rasters that are not fixtures"""
+    try:
+        import numba  # noqa: F401
+    except ImportError:
+        pytest.skip('numba missing: the reference cannot run here')
+    from oracle import stats_oracle
+    rng = numpy.random.default_rng(seed)
+    (nR, nC) = (150, 170)
+    coarse = rng.integers(1, 400, (nR // 7 + 2, nC // 9 + 2))
+    seg = numpy.kron(coarse, numpy.ones((7, 9), dtype=numpy.int64))[:nR, :nC]
+    seg[rng.random((nR, nC)) < 0.04] = 0
+    (_, inv) = numpy.unique(numpy.concatenate([[0], seg.ravel()]), return_inverse=True)
+    seg = inv[1:].reshape(nR, nC).astype(numpy.uint32)       # ids 1..n without gaps, 0 = null
+    info = numpy.iinfo(dtype)
+    img = rng.integers(max(info.min, -30000), min(int(info.max), 3000000000) + 1, (nR, nC)).astype(dtype)
+    img[seg % 4 == 0] = (img[seg % 4 == 0] % 7).astype(dtype)          # few distinct values: mode ties
+    if imgNull is not None:
+        img[rng.random((nR, nC)) < 0.1] = imgNull
+        img[seg == 3] = imgNull
+    sel = [('mn', 'min'), ('mx', 'max'), ('mean', 'mean'), ('sd', 'stddev'), ('med', 'median'), ('mode', 'mode'),
+        ('p10', 'percentile', 10), ('p0', 'percentile', 0), ('p100', 'percentile', 100), ('n', 'pixcount')]
+    npz = str(tmp_path / 'in.npz')
+    out = str(tmp_path / 'out.npz')
+    numpy.savez(npz, seg=seg, img=img)
+    spec = {'npz': npz, 'out': out, 'imgNull': imgNull, 'missing': -9999, 'selection': [list(s) for s in sel]}
+    specFile = str(tmp_path / 'spec.json')
+    json.dump(spec, open(specFile, 'w'))
+    runner = str(tmp_path / 'runner.py')
+    open(runner, 'w').write(STATS_RUNNER % {'ref': REFERENCE, 'golden': os.path.join(ROOT, 'tests', 'golden')})
+    env = dict(os.environ, NUMBA_CACHE_DIR=str(tmp_path / 'nbcache'))
+    subprocess.run([sys.executable, runner, specFile], check=True, env=env, timeout=1200,
+        stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    want = numpy.load(out)
+    got = stats_oracle.calcPerSegmentStats(img, seg, sel, -9999, imgNull)
+    for s in sel:
+        assert got[s[0]].dtype == want[s[0]].dtype, s[0]
+        assert numpy.array_equal(got[s[0]], want[s[0]]), '%s differs at %s' % (s[0],
+            numpy.flatnonzero(got[s[0]] != want[s[0]])[:5])
