@@ -64,7 +64,11 @@ WORKLOAD = {
 METRIC = 'Mpixels/sec full segmentation (assign+clump+eliminate+stitch), tiled 10980x10980x4 uint16'
 UNIT = 'Mpixel/s'
 E2E_WORKERS = int(os.environ.get('BENCH_E2E_WORKERS', '3'))   # segmentation workers of the host-to-host run
-SCENE_GRID = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}   # scenes (rows, cols) of the mosaic per N
+# scenes (rows, cols) of the weak-scaling mosaic per N: side by side.  A row of scenes keeps two tile rows
+# (4096 and 7908 pixels high, as in the single scene), 1.40-1.43 tile pixels per unique pixel and two
+# rim tiles per rank boundary; the squarer 2 x 2 / 2 x 4 layouts measured in profiles/r2_scaling.md have
+# six tile rows, 1.52-1.58 tile pixels per unique pixel and six rim tiles per boundary
+SCENE_GRID = {1: (1, 1), 2: (1, 2), 4: (1, 4), 8: (1, 8)}
 RESIDENT_WORKERS = int(os.environ.get('BENCH_RESIDENT_WORKERS', '2'))   # 0: segment and stitch in one thread
 
 # algorithmic bytes per pixel of the kernels:
