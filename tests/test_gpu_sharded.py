@@ -68,6 +68,8 @@ def test_two_ranks_equal_reference_mosaic(name):
     assert int(maxSegId) == c['meta']['maxSegId']
     assert numpy.array_equal(mosaic, c['mosaic'])
     assert numpy.array_equal(numpy.asarray(hist), c['hist'])
+    # the offsets came from the per-tile steps the device reported (no replay of the sequential order)
+    assert not usedFallback
 
 
 def _rank_main_api(rank, world, port, name, resq):
