@@ -149,6 +149,10 @@ CASES = [
     # inherited around corners across rank boundaries (several look-up rounds)
     ('w4_6x6', 4, ('segmented', 16, 420, 430, 96, 32, False), False),
     ('w8_blobby_7x6', 8, ('blobby', 17, 400, 460, 96, 32, False), False),
+    # a row of scenes (bench.py's weak-scaling mosaic): two tile rows, many tile columns, a rank owns
+    # whole columns plus a partial one at either end
+    ('w8_row_of_scenes', 8, ('segmented', 18, 343, 1900, 128, 32, False), False),
+    ('w4_row_of_scenes_blobby', 4, ('blobby', 19, 343, 1300, 128, 32, False), False),
 ]
 
 
