@@ -72,6 +72,18 @@ def test_two_ranks_equal_reference_mosaic(name):
     assert not usedFallback
 
 
+def _case(name):
+    """a golden fixture, or 'row_of_scenes': a seeded raster with two tile rows and many tile
+    columns (the shape of bench.py's weak-scaling mosaic), no reference mosaic"""
+    if name != 'row_of_scenes':
+        return goldenutil.load(name)
+    from pyshepseg_b200 import synth
+    img = synth.synth_v1(686, 2900, 3, seed=77, cell=14)
+    meta = {'tileSize': 256, 'overlapSize': 64, 'minSegmentSize': 20, 'numClusters': 16, 'imgNullVal': None,
+        'fourConnected': True, 'simpleTileRecode': False}
+    return {'img': img, 'centres': synth.diagonal_centres(img, 16), 'meta': meta}
+
+
 def _rank_main_api(rank, world, port, name, resq):
     """the same through the public function: every rank hands doTiledShepherdSegmentation the
     WINDOW of the raster its tiles cover (row and column offsets) and a sink of that window"""
@@ -79,7 +91,7 @@ def _rank_main_api(rank, world, port, name, resq):
     from pyshepseg_b200 import tiling, distributed, rasterfile
     dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
     try:
-        c = goldenutil.load(name)
+        c = _case(name)
         m = c['meta']
         img = c['img']
         (nB, nR, nC) = img.shape
@@ -129,4 +141,31 @@ def test_two_ranks_through_the_public_function(name):
     assert numpy.array_equal(mosaic, c['mosaic'])
     assert numpy.array_equal(hist, c['hist'])
     assert statMax == repr(c['meta']['maxSegId'])
+
+
+def test_four_ranks_row_of_scenes_equal_one_rank():
+    """four ranks on a mosaic of two tile rows and many columns (a rank owns whole tile columns plus
+    a partial one at either end; strips exchanged mid-run) against the same call on one rank"""
+    import torch.multiprocessing as mp
+    from pyshepseg_b200 import tiling, rasterfile
+    c = _case('row_of_scenes')
+    m = c['meta']
+    ti = tiling.getTilesForFile((c['img'].shape[2], c['img'].shape[1]), m['tileSize'], m['overlapSize'])
+    assert ti.nrows == 2 and ti.ncols >= 12
+    one = tiling.doTiledShepherdSegmentation(rasterfile.MemoryRaster(c['img']), None, tileSize=m['tileSize'],
+        overlapSize=m['overlapSize'], minSegmentSize=m['minSegmentSize'], numClusters=m['numClusters'],
+        fourConnected=True, kmeansObj=goldenutil.Centres(c['centres']), outputDriver='MEM', returnGDALDS=True)
+    ctx = mp.get_context('spawn')
+    resq = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_rank_main_api, args=(r, 4, port, 'row_of_scenes', resq)) for r in range(4)]
+    for p in procs:
+        p.start()
+    (maxSegId, mosaic, hist, statMax, launches) = resq.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert maxSegId == int(one.maxSegId) and maxSegId > 1000
+    assert numpy.array_equal(mosaic, one.outDs.array)
+    assert numpy.array_equal(hist, numpy.asarray(one.outDs.hist))
 
