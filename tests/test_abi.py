@@ -48,3 +48,33 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(d, f)).read()
                 assert 'oracle' not in src.replace('the oracle', '').replace('oracle /', '').replace(
                     "oracle's", ''), f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof and the offset of every field of the three structures that cross the boundary: the
+    header compiled by gcc (plain C, which also shows the header is C, not C++) against the ctypes
+    declarations in pyshepseg_b200/_lib.py"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc is not installed')
+    structs = (('ssg_tile_params', _lib.TileParams), ('ssg_tile_result', _lib.TileResult),
+        ('ssg_tile_tables', _lib.TileTables))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "shepseg_b200.h"', 'int main(void) {']
+    for (cname, cls) in structs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for (field, _) in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, field, cname, field))
+    lines += ['printf("abi %d\\n", SSG_ABI_VERSION);', 'return 0; }']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = str(tmp_path / 'layout')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', exe],
+        check=True)
+    got = dict(l.rsplit(' ', 1) for l in subprocess.run([exe], check=True, stdout=subprocess.PIPE
+        ).stdout.decode().splitlines())
+    for (cname, cls) in structs:
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for (field, _) in cls._fields_:
+            assert int(got['%s.%s' % (cname, field)]) == getattr(cls, field).offset, (cname, field)
+    assert int(got['abi']) == _lib.ABI_VERSION
