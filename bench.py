@@ -452,7 +452,7 @@ def workload_config(wl, gpus, shape=None, tileInfo=None):
         'maxSpectralDiff': wl['maxSpectralDiff'], 'fourConnected': wl['fourConnected'],
         'scenes': 1 if wl.get('strong') else gpus,
         'parallelism': (('one mosaic, the same for every N, ' if wl.get('strong') else 'one mosaic of %d scenes, ' % gpus) +
-            'tiles dealt over %d GPUs in row-major chunks, overlap strips over NCCL, ids global' % gpus)
+            'tiles dealt over %d GPUs in blocks of tile columns of equal cost, overlap strips over NCCL, ids global' % gpus)
             if gpus > 1 else 'single GPU',
         'l2_policy': 'inputs larger than L2 (964 MB raster, 482 MB mosaic per scene)'}
 
